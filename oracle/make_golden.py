@@ -1,0 +1,144 @@
+"""Generate tests/golden/*.npz by executing the UNMODIFIED reference (build container only).
+
+    python -m oracle.make_golden
+
+Each fixture stores its inputs next to the reference's outputs, so the GPU box (which has no
+/root/reference) can replay them.  Reference entry points executed verbatim:
+  * ``src/retrievers/bm25.py``  TFIDF / BM25 / AtireBM25 ``.search_all``          (bm25.py:33-173)
+  * ``src/retrievers/hybrid.py`` ``Aggregator.fuse``                              (hybrid.py:166-307)
+  * ``src/retrievers/splade/base.py`` ``BaseModel.search`` with injected embeddings (base.py:199-251)
+"""
+from __future__ import annotations
+
+import contextlib
+import io
+import os
+
+import numpy as np
+import torch
+
+from fusion_b200 import synth
+from oracle import ref_loader
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def _quiet(fn, *a, **k):
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf), contextlib.redirect_stderr(buf):
+        return fn(*a, **k)
+
+
+def golden_lexical():
+    mod = ref_loader.load_bm25()
+    # --- small adversarial corpus: negative idf (df > N/2), OOV, repeated tokens, < k matches
+    rng = np.random.Generator(np.random.PCG64(7))
+    n_docs, vocab = 600, 800
+    dptr, dtok = synth.lexical_corpus(n_docs, vocab, 1.1, 3.0, 0.6, 3, 120, seed=11)
+    # force term 0 into 80% of the docs (negative BM25 idf) and make two docs identical (tie on every query)
+    first = dptr[:-1][rng.random(n_docs) < 0.8]
+    dtok[first] = 0
+    l0, l1 = dptr[5], dptr[6]
+    n_copy = min(dptr[6] - dptr[5], dptr[8] - dptr[7])
+    qptr, qtok = synth.lexical_queries(24, vocab, 1.1, 4.0, seed=12, oov_every=5)
+    docs = synth.ids_to_strings(dptr, dtok)
+    docs[7] = docs[5]                       # exact duplicate document => exact score ties
+    queries = synth.ids_to_strings(qptr, qtok)
+    queries[1] = "t0"                       # only the negative-idf term
+    queries[2] = "t3 t3 t9 t3"              # repeated tokens
+    queries[3] = "zzz yyy"                  # nothing matches: all scores 0 -> doc order
+    queries[4] = "t799 t0"                  # rare + negative
+    out = {"docs": np.array(docs), "queries": np.array(queries)}
+    for name, cls, kw in (("tfidf", mod.TFIDF, {}), ("bm25", mod.BM25, dict(k1=2.5, b=0.2)),
+                          ("bm25_mm", mod.BM25, dict(k1=0.9, b=0.4)), ("atire", mod.AtireBM25, dict(k1=0.9, b=0.4))):
+        r = _quiet(cls, docs, **kw)
+        res = _quiet(r.search_all, queries, top_k=n_docs)
+        out[f"{name}_ids"] = np.array([[x["corpus_id"] for x in q] for q in res], dtype=np.int32)
+        out[f"{name}_scores"] = np.array([[x["score"] for x in q] for q in res], dtype=np.float64)
+    np.savez_compressed(os.path.join(OUT, "lexical_small.npz"), **out)
+
+    # --- C1-shaped slice: 4,000 docs of the LLeQA-shaped generator, 16 queries, top-200, k1=2.5 b=0.2
+    (dptr, dtok), (qptr, qtok) = synth.c1_lexical(n_docs=4000, n_queries=16)
+    docs, queries = synth.ids_to_strings(dptr, dtok), synth.ids_to_strings(qptr, qtok)
+    r = _quiet(mod.BM25, docs, k1=2.5, b=0.2)
+    res = _quiet(r.search_all, queries, top_k=200)
+    np.savez_compressed(
+        os.path.join(OUT, "lexical_c1_slice.npz"), n_docs=4000, n_queries=16, top_k=200,
+        ids=np.array([[x["corpus_id"] for x in q] for q in res], dtype=np.int32),
+        scores=np.array([[x["score"] for x in q] for q in res], dtype=np.float64))
+
+
+def _ranked_lists(rng, n_q, n, pool, dup=False, const=False):
+    out = []
+    for _ in range(n_q):
+        ids = rng.choice(pool, size=n, replace=False)
+        sc = np.sort(rng.normal(0, 3, n))[::-1]
+        if const:
+            sc = np.full(n, 1.25)
+        if dup:
+            ids[n // 2] = ids[1]          # repeated id inside one list
+        out.append([{"corpus_id": int(i), "score": float(s)} for i, s in zip(ids, sc)])
+    return out
+
+
+def golden_fusion():
+    mod = ref_loader.load_hybrid()
+    rng = np.random.Generator(np.random.PCG64(21))
+    n_q, n, pool = 6, 60, 150
+    lists = {"bm25": _ranked_lists(rng, n_q, n, pool, dup=True),
+             "dpr": _ranked_lists(rng, n_q, n - 7, pool),
+             "splade": _ranked_lists(rng, n_q, n, pool, const=True)}
+    # fp32-exact dense-like scores for one system (as produced by .tolist() of an fp32 tensor)
+    for q in lists["dpr"]:
+        for x in q:
+            x["score"] = float(np.float32(x["score"] * 0.01))
+    weights = {"bm25": 0.5, "dpr": 0.3, "splade": 0.2}
+    distrs = {k: np.quantile(rng.normal(0, 3, 5000), np.linspace(0, 1, 101)) for k in lists}
+    out = {"systems": np.array(list(lists)), "weights": np.array([weights[k] for k in lists])}
+    for k, v in lists.items():
+        L = max(len(q) for q in v)
+        out[f"in_ids_{k}"] = np.array([[x["corpus_id"] for x in q] for q in v], dtype=np.int32)
+        out[f"in_scores_{k}"] = np.array([[x["score"] for x in q] for q in v], dtype=np.float64)
+        out[f"distr_{k}"] = distrs[k]
+    import copy
+    cases = [("bcf", None), ("rrf", None)] + [("nsf", nm) for nm in
+             ("none", "min-max", "z-score", "arctan", "percentile-rank", "normal-curve-equivalent")]
+    for method, norm in cases:
+        res = mod.Aggregator.fuse(copy.deepcopy(lists), method=method, normalization=norm,
+                                  linear_weights=weights, percentile_distributions=distrs)
+        tag = method if norm is None else f"{method}_{norm}"
+        L = max(len(q) for q in res)
+        ids = np.full((n_q, L), -1, dtype=np.int32)
+        sc = np.full((n_q, L), np.nan, dtype=np.float64)
+        for qi, q in enumerate(res):
+            ids[qi, :len(q)] = [x["corpus_id"] for x in q]
+            sc[qi, :len(q)] = [float(x["score"]) for x in q]
+        out[f"out_ids_{tag}"], out[f"out_scores_{tag}"] = ids, sc
+        out[f"out_dtype_{tag}"] = np.array(type(res[0][0]["score"]).__name__)
+    np.savez_compressed(os.path.join(OUT, "fusion_small.npz"), **out)
+
+
+def golden_dense():
+    q = torch.from_numpy(synth.dense_embeddings(7, 64, seed=31))
+    d = torch.from_numpy(synth.dense_embeddings(3000, 64, seed=32))
+    d[11] = d[10]                          # exact tie
+    out = {"q": q.numpy(), "d": d.numpy()}
+    for sim in ("cos_sim", "dot"):
+        m = ref_loader.make_injected_searcher(sim, q, d)
+        res = m.search(["x"] * 7, ["y"] * 3000, query_chunk_size=3, doc_chunk_size=1000, topk=50)
+        out[f"{sim}_ids"] = np.array([[x["doc_id"] for x in r] for r in res], dtype=np.int32)
+        out[f"{sim}_scores"] = np.array([[x["score"] for x in r] for r in res], dtype=np.float64)
+    np.savez_compressed(os.path.join(OUT, "dense_small.npz"), **out)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    golden_lexical()
+    golden_fusion()
+    golden_dense()
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()

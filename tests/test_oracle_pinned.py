@@ -1,0 +1,84 @@
+"""The oracle restatements against fixtures produced by the UNMODIFIED reference (oracle/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from fusion_b200 import synth
+from oracle import bm25 as obm25
+from oracle import dense as odense
+from oracle import fusion as ofusion
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+@pytest.mark.parametrize("tag,variant,k1,b", [("tfidf", "tfidf", 0, 0), ("bm25", "bm25", 2.5, 0.2),
+                                              ("bm25_mm", "bm25", 0.9, 0.4), ("atire", "atire", 0.9, 0.4)])
+def test_lexical_small_bit_exact(golden_dir, tag, variant, k1, b):
+    g = _load(golden_dir, "lexical_small.npz")
+    docs, queries = [str(x) for x in g["docs"]], [str(x) for x in g["queries"]]
+    o = obm25.LexicalOracle.from_strings(docs, variant, k1, b)
+    for qi, q in enumerate(queries):
+        ids, sc = o.search_ids(o.query_ids(q), len(docs))
+        assert np.array_equal(ids, g[f"{tag}_ids"][qi]), (tag, qi)
+        assert np.array_equal(sc, g[f"{tag}_scores"][qi]), (tag, qi)      # bit-exact fp64
+
+
+def test_lexical_c1_slice_bit_exact(golden_dir):
+    g = _load(golden_dir, "lexical_c1_slice.npz")
+    (dptr, dtok), (qptr, qtok) = synth.c1_lexical(n_docs=int(g["n_docs"]), n_queries=int(g["n_queries"]))
+    docs, queries = synth.ids_to_strings(dptr, dtok), synth.ids_to_strings(qptr, qtok)
+    o = obm25.LexicalOracle.from_strings(docs, "bm25", 2.5, 0.2)
+    for qi, q in enumerate(queries):
+        ids, sc = o.search_ids(o.query_ids(q), int(g["top_k"]))
+        assert np.array_equal(ids, g["ids"][qi])
+        assert np.array_equal(sc, g["scores"][qi])
+
+
+def test_lexical_token_id_path_matches_string_path():
+    (dptr, dtok), (qptr, qtok) = synth.c1_lexical(n_docs=500, n_queries=8, vocab=300)
+    docs = synth.ids_to_strings(dptr, dtok)
+    a = obm25.LexicalOracle.from_strings(docs, "bm25", 0.9, 0.4)
+    b = obm25.LexicalOracle(dptr, dtok, 300, "bm25", 0.9, 0.4)
+    for qi in range(8):
+        toks = qtok[qptr[qi]:qptr[qi + 1]]
+        q = " ".join(f"t{t}" for t in toks)
+        ia, sa = a.search_ids(a.query_ids(q), 500)
+        ib, sb = b.search_ids(np.where(toks < 300, toks, -1), 500)
+        assert np.array_equal(ia, ib) and np.array_equal(sa, sb)
+
+
+FUSION_CASES = [("bcf", None), ("rrf", None)] + [("nsf", n) for n in ofusion.NORMALIZATIONS]
+
+
+@pytest.mark.parametrize("method,norm", FUSION_CASES)
+def test_fusion_small(golden_dir, method, norm):
+    g = _load(golden_dir, "fusion_small.npz")
+    systems = [str(s) for s in g["systems"]]
+    tag = method if norm is None else f"{method}_{norm}"
+    exp_ids, exp_sc = g[f"out_ids_{tag}"], g[f"out_scores_{tag}"]
+    for qi in range(exp_ids.shape[0]):
+        ids, sc = ofusion.fuse_query([g[f"in_ids_{s}"][qi] for s in systems], [g[f"in_scores_{s}"][qi] for s in systems],
+                                     method, norm, list(g["weights"]), [g[f"distr_{s}"] for s in systems])
+        n = int((exp_ids[qi] >= 0).sum())
+        assert ids == exp_ids[qi, :n].tolist(), (tag, qi)
+        np.testing.assert_allclose(np.asarray(sc, dtype=np.float64), exp_sc[qi, :n], rtol=0, atol=0, equal_nan=True)
+
+
+@pytest.mark.parametrize("sim", ["cos_sim", "dot"])
+def test_dense_small(golden_dir, sim):
+    g = _load(golden_dir, "dense_small.npz")
+    q, d = torch.from_numpy(g["q"]), torch.from_numpy(g["d"])
+    res = odense.semantic_search(q, d, 50, sim=sim, query_chunk_size=3, corpus_chunk_size=1000, key="doc_id")
+    sc, ids = odense.topk_tensors(q, d, 50, sim=sim, chunk=700)
+    for qi in range(7):
+        got_ids = [x["doc_id"] for x in res[qi]]
+        got_sc = np.array([x["score"] for x in res[qi]])
+        np.testing.assert_array_equal(got_sc, g[f"{sim}_scores"][qi])
+        assert sorted(got_ids) == sorted(g[f"{sim}_ids"][qi].tolist())
+        # tensor form: same scores to fp32 rounding, same id set
+        np.testing.assert_allclose(sc[qi].numpy(), g[f"{sim}_scores"][qi], rtol=2e-6, atol=2e-6)
+        assert sorted(ids[qi].tolist()) == sorted(g[f"{sim}_ids"][qi].tolist())
