@@ -1,0 +1,409 @@
+// K1: exhaustive dense inner-product scoring with the top-k fused into the tcgen05 GEMM epilogue.
+//
+// scores[q, n] = <Q[q,:], D[n,:]> is a [Qn x dim] x [dim x Nn] GEMM (9.5e13 FLOP for 6,980 x 8.8M x 768) whose
+// 245 GB result must never reach HBM.  A warp-specialised persistent kernel (TMA producer warp, single-thread
+// tcgen05.mma issuer, four epilogue warps reading the fp32 accumulators back from TMEM) filters every score
+// against the query's running threshold and appends the few survivors to per-query candidate buffers
+// (topk_state.cuh).  The corpus is swept in rounds of geometrically growing doc ranges; between rounds
+// cand_select tightens the thresholds.  In the exact mode the bf16 tensor-core scores only FILTER: everything
+// within `margin` of the running k-th score is kept and rescored in fp32 on CUDA cores from the fp32 originals,
+// and the final top-k is taken from the exact scores.
+//
+// Replaces: sentence_transformers.util.semantic_search (src/retrievers/hybrid.py:103),
+// BaseModel.search (src/retrievers/splade/base.py:199-251), compute_metrices scoring loop
+// (src/utils/sentence_transformers.py:334-364).
+#include "common.cuh"
+#include "ptx.cuh"
+#include "topk_state.cuh"
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <limits>
+
+namespace fz {
+
+// ----------------------------------------------------------------------------------- tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// 2D bf16 row-major [rows, cols] tensor, box = [box_rows, 64 cols] (128 bytes wide), 128-byte swizzle.
+int make_bf16_tile_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    FZ_REQUIRE(fn, "cuTensorMapEncodeTiled is not available from the driver");
+    FZ_REQUIRE(((uintptr_t)base & 15) == 0 && (cols * 2) % 16 == 0, "tensor base / row pitch must be 16-byte aligned");
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {cols * 2};
+    cuuint32_t box[2] = {64, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    FZ_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return FZ_OK;
+}
+
+// ----------------------------------------------------------------------------------- filter GEMM
+constexpr int kBM = 128;          // queries per tile  (UMMA M)
+constexpr int kBN = 256;          // docs per tile     (UMMA N)
+constexpr int kBK = 64;           // bf16 elements per k-block = one 128-byte swizzle row
+constexpr int kStages = 4;
+constexpr int kABytes = kBM * kBK * 2;   // 16 KB
+constexpr int kBBytes = kBN * kBK * 2;   // 32 KB
+constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kGemmThreads = 256;        // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps4-7 epilogue
+constexpr int kTmemCols = 512;           // two 256-column fp32 accumulators
+constexpr size_t kGemmSmem = (size_t)kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+
+struct GemmArgs {
+    int n_queries;
+    long long r_lo, r_hi;    // doc rows of this round
+    int num_k_blocks;
+    int m_tiles, n_tiles;
+    CandState<float> st;
+};
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+dense_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_d,
+                    const GemmArgs G) {
+    extern __shared__ unsigned char smem_dyn[];
+    // 1024-byte alignment: required by the 128-byte swizzle atoms the UMMA descriptors assume
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * kStageBytes);
+    uint64_t* full_bar = bars;                     // [kStages]  TMA -> MMA
+    uint64_t* empty_bar = bars + kStages;          // [kStages]  MMA -> TMA
+    uint64_t* tfull_bar = bars + 2 * kStages;      // [2]        MMA -> epilogue
+    uint64_t* tempty_bar = bars + 2 * kStages + 2; // [2]        epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total_tiles = G.m_tiles * G.n_tiles;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&tmap_q);
+        ptx::prefetch_tensormap(&tmap_d);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < kStages; ++i) {
+            ptx::mbar_init(&full_bar[i], 1);
+            ptx::mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(&tfull_bar[i], 1);
+            ptx::mbar_init(&tempty_bar[i], 4);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 2) {
+        ptx::tmem_alloc(tmem_slot, kTmemCols);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================================ TMA producer (one elected lane) ================================
+        if (ptx::elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int n_t = tile / G.m_tiles, m_t = tile - n_t * G.m_tiles;
+                const int q0 = m_t * kBM;
+                const long long d0 = G.r_lo + (long long)n_t * kBN;
+                for (int kb = 0; kb < G.num_k_blocks; ++kb) {
+                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    unsigned char* sa = smem + (size_t)stage * kStageBytes;
+                    ptx::mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
+                    ptx::tma_load_2d(sa, &tmap_q, &full_bar[stage], kb * kBK, q0);
+                    ptx::tma_load_2d(sa + kABytes, &tmap_d, &full_bar[stage], kb * kBK, (int32_t)d0);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer (one elected lane) ===================================
+        if (ptx::elect_one()) {
+            const uint32_t idesc = ptx::make_idesc_bf16(kBM, kBN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                const int buf = it & 1;
+                ptx::mbar_wait(&tempty_bar[buf], ((it >> 1) & 1) ^ 1);   // epilogue drained this accumulator
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)buf * kBN;
+                for (int kb = 0; kb < G.num_k_blocks; ++kb) {
+                    ptx::mbar_wait(&full_bar[stage], phase);
+                    ptx::tc_fence_after();
+                    const uint32_t sa = ptx::smem_u32(smem + (size_t)stage * kStageBytes);
+                    const uint32_t sb = sa + kABytes;
+#pragma unroll
+                    for (int k = 0; k < kBK / 16; ++k) {
+                        const uint64_t da = ptx::make_smem_desc_sw128(sa + k * 32);
+                        const uint64_t db = ptx::make_smem_desc_sw128(sb + k * 32);
+                        ptx::mma_bf16_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    ptx::mma_commit(&empty_bar[stage]);     // smem stage reusable once these MMAs retire
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+                ptx::mma_commit(&tfull_bar[buf]);           // accumulator complete
+            }
+        }
+    } else if (warp >= 4) {
+        // ================================ epilogue: TMEM -> threshold filter -> candidate append ==========
+        const int ew = warp - 4;                            // == warp % 4: the TMEM lane quarter this warp may read
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int n_t = tile / G.m_tiles, m_t = tile - n_t * G.m_tiles;
+            const int buf = it & 1;
+            const int q = m_t * kBM + ew * 32 + lane;
+            const long long d0 = G.r_lo + (long long)n_t * kBN;
+            const int limit = (int)min((long long)kBN, G.r_hi - d0);
+            const bool q_ok = q < G.n_queries;
+            const float tau = q_ok ? G.st.tau[q] : std::numeric_limits<float>::infinity();
+            ptx::mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
+            ptx::tc_fence_after();
+            const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)buf * kBN;
+#pragma unroll 1
+            for (int c = 0; c < kBN / 32; ++c) {
+                uint32_t r[32];
+                ptx::tmem_ld_32x32(t_row + c * 32, r);
+                ptx::tmem_ld_wait();
+                uint32_t mask = 0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float v = __uint_as_float(r[j]);
+                    if (v > tau && c * 32 + j < limit) mask |= 1u << j;
+                }
+                if (mask) {
+                    const int cnt = __popc(mask);
+                    int base = atomicAdd(&G.st.cnt[q], cnt);
+                    const size_t off = (size_t)q * G.st.cap;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if (mask & (1u << j)) {
+                            if (base < G.st.cap) {
+                                G.st.score[off + base] = __uint_as_float(r[j]);
+                                G.st.id[off + base] = (int32_t)(d0 + c * 32 + j);
+                            }
+                            ++base;
+                        }
+                    }
+                }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tempty_bar[buf]);
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) ptx::tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ----------------------------------------------------------------------------------- fp32 rescoring
+// One warp per (query, kept candidate): exact fp32 dot product from the fp32 originals, in place.
+constexpr int kRescoreWarps = 8;
+__global__ void __launch_bounds__(kRescoreWarps * 32)
+rescore_kernel(const float* __restrict__ qf, const float* __restrict__ df, int dim, CandState<float> st) {
+    extern __shared__ __align__(16) float qs[];
+    const int q = blockIdx.x;
+    for (int i = threadIdx.x; i < dim; i += blockDim.x) qs[i] = qf[(size_t)q * dim + i];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = min(st.cnt[q], st.cap);
+    const size_t off = (size_t)q * st.cap;
+    for (int i = warp; i < n; i += kRescoreWarps) {
+        const float* __restrict__ d = df + (size_t)st.id[off + i] * dim;
+        float acc = 0.f;
+        if ((dim & 3) == 0) {
+            const float4* d4 = reinterpret_cast<const float4*>(d);
+            const float4* q4 = reinterpret_cast<const float4*>(qs);
+            for (int j = lane; j < dim / 4; j += 32) {
+                const float4 a = __ldg(d4 + j), b = q4[j];
+                acc = fmaf(a.x, b.x, acc);
+                acc = fmaf(a.y, b.y, acc);
+                acc = fmaf(a.z, b.z, acc);
+                acc = fmaf(a.w, b.w, acc);
+            }
+        } else {
+            for (int j = lane; j < dim; j += 32) acc = fmaf(d[j], qs[j], acc);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) st.score[off + i] = acc;
+    }
+}
+
+// ----------------------------------------------------------------------------------- exact fp32 scores (full mode)
+// Plain SIMT tiled GEMM: out[q, n] = sum_k Q[q,k] * D[n,k], fp32 FMA in k order.  Used for the reference's
+// "rank every document" mode on small corpora (src/retrievers/hybrid.py:103 with top_k = N), where the whole
+// score matrix is wanted anyway.
+constexpr int kFT = 64, kFK = 16;
+__global__ void __launch_bounds__(256) dense_scores_kernel(const float* __restrict__ Q, const float* __restrict__ D,
+                                                           int nq, long long nd, int dim, float* __restrict__ out) {
+    __shared__ float qs[kFK][kFT + 1];
+    __shared__ float ds[kFK][kFT + 1];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const long long n0 = (long long)blockIdx.x * kFT;
+    const int q0 = blockIdx.y * kFT;
+    float acc[4][4] = {};
+    for (int k0 = 0; k0 < dim; k0 += kFK) {
+        for (int i = threadIdx.x; i < kFT * kFK; i += 256) {
+            const int r = i / kFK, c = i - r * kFK;
+            const int k = k0 + c;
+            qs[c][r] = (q0 + r < nq && k < dim) ? Q[(size_t)(q0 + r) * dim + k] : 0.f;
+            ds[c][r] = (n0 + r < nd && k < dim) ? D[(size_t)(n0 + r) * dim + k] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kFK; ++k) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { a[i] = qs[k][ty * 4 + i]; b[i] = ds[k][tx * 4 + i]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            const int q = q0 + ty * 4 + i;
+            const long long n = n0 + tx * 4 + j;
+            if (q < nq && n < nd) out[(size_t)q * nd + n] = acc[i][j];
+        }
+}
+
+// ----------------------------------------------------------------------------------- row normalisation
+__global__ void normalize_rows_kernel(const float* __restrict__ x, long long n_rows, int dim, int normalize,
+                                      float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n_rows) return;
+    const float* r = x + (size_t)row * dim;
+    float nrm = 1.f;
+    if (normalize) {
+        float ss = 0.f;
+        for (int j = lane; j < dim; j += 32) ss = fmaf(r[j], r[j], ss);
+        ss = warp_sum(ss);
+        nrm = fmaxf(sqrtf(ss), 1e-12f);       // x / max(||x||, eps)
+    }
+    for (int j = lane; j < dim; j += 32) {
+        const float v = normalize ? __fdiv_rn(r[j], nrm) : r[j];
+        if (out_f32) out_f32[(size_t)row * dim + j] = v;
+        if (out_bf16) out_bf16[(size_t)row * dim + j] = __float2bfloat16_rn(v);
+    }
+}
+
+}  // namespace fz
+
+using namespace fz;
+
+extern "C" {
+
+size_t fz_dense_topk_workspace_bytes(int n_queries, int k, int cap) {
+    (void)k;
+    return cand_state_bytes<float>(n_queries, cap);
+}
+
+int fz_dense_topk(const void* q_bf16, const void* d_bf16, const float* q_f32, const float* d_f32, int n_queries,
+                  int64_t n_docs, int dim, int k, float margin, int64_t doc_base, int cap, int growth,
+                  float* out_scores, int32_t* out_ids, int32_t* out_status, void* ws, size_t ws_bytes,
+                  fz_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    FZ_REQUIRE(q_bf16 && d_bf16 && out_scores && out_ids && out_status, "null pointer");
+    FZ_REQUIRE((q_f32 == nullptr) == (d_f32 == nullptr), "q_f32 and d_f32 must both be given (exact) or both NULL (bf16)");
+    FZ_REQUIRE(dim >= 64 && dim % 64 == 0, "dim=%d must be a positive multiple of 64 (pad with zeros)", dim);
+    FZ_REQUIRE(n_docs >= 1 && n_docs < (1ll << 31), "n_docs out of range");
+    FZ_REQUIRE(k >= 1 && cap >= 2 * k && cap <= 8192, "need 1 <= k, 2k <= cap <= 8192 (k=%d cap=%d)", k, cap);
+    FZ_REQUIRE(growth >= 1 && growth <= 64, "growth=%d out of range", growth);
+    FZ_REQUIRE(margin >= 0.f, "margin must be >= 0");
+    FZ_REQUIRE(ws && ws_bytes >= cand_state_bytes<float>(n_queries, cap), "workspace too small");
+    if (n_queries == 0) return FZ_OK;
+
+    CUtensorMap tmap_q, tmap_d;
+    int rc = make_bf16_tile_map(&tmap_q, q_bf16, (uint64_t)n_queries, (uint64_t)dim, kBM);
+    if (rc) return rc;
+    rc = make_bf16_tile_map(&tmap_d, d_bf16, (uint64_t)n_docs, (uint64_t)dim, kBN);
+    if (rc) return rc;
+    static bool attr = false;
+    if (!attr) {
+        FZ_CUDA(cudaFuncSetAttribute(dense_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
+        attr = true;
+    }
+
+    GemmArgs G;
+    memset(&G, 0, sizeof(G));
+    G.n_queries = n_queries;
+    G.num_k_blocks = dim / kBK;
+    G.m_tiles = ceil_div(n_queries, kBM);
+    G.st = cand_state_carve<float>(ws, n_queries, cap, out_status);
+    rc = cand_init<float>(G.st, n_queries, stream);
+    if (rc) return rc;
+
+    const bool exact = d_f32 != nullptr;
+    long long lo = 0, hi = n_docs < cap ? n_docs : cap;
+    while (true) {
+        G.r_lo = lo;
+        G.r_hi = hi;
+        G.n_tiles = (int)ceil_div<long long>(hi - lo, kBN);
+        const long long tiles = (long long)G.m_tiles * G.n_tiles;
+        const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+        dense_filter_kernel<<<grid, kGemmThreads, kGemmSmem, stream>>>(tmap_q, tmap_d, G);
+        FZ_LAUNCH_CHECK();
+        const bool last = hi >= n_docs;
+        rc = cand_select<float>(G.st, n_queries, k, margin, last && !exact, doc_base, out_scores, out_ids, nullptr, stream);
+        if (rc) return rc;
+        if (last) break;
+        lo = hi;
+        hi = growth >= 2 ? hi * growth : hi + (cap - k);
+        if (hi > n_docs) hi = n_docs;
+    }
+    if (exact) {
+        rescore_kernel<<<n_queries, kRescoreWarps * 32, (size_t)dim * sizeof(float), stream>>>(q_f32, d_f32, dim, G.st);
+        FZ_LAUNCH_CHECK();
+        rc = cand_select<float>(G.st, n_queries, k, 0.f, true, doc_base, out_scores, out_ids, nullptr, stream);
+        if (rc) return rc;
+    }
+    return FZ_OK;
+}
+
+int fz_dense_scores_f32(const float* q_f32, const float* d_f32, int n_queries, int64_t n_docs, int dim,
+                        float* out_scores, fz_stream_t stream) {
+    FZ_REQUIRE(q_f32 && d_f32 && out_scores, "null pointer");
+    FZ_REQUIRE(dim >= 1 && n_docs >= 1, "bad sizes");
+    if (n_queries == 0) return FZ_OK;
+    dim3 grid((unsigned)ceil_div<long long>(n_docs, kFT), (unsigned)ceil_div(n_queries, kFT));
+    dense_scores_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(q_f32, d_f32, n_queries, n_docs, dim, out_scores);
+    FZ_LAUNCH_CHECK();
+    return FZ_OK;
+}
+
+int fz_normalize_rows(const float* x, int64_t n_rows, int dim, int normalize, float* out_f32, void* out_bf16,
+                      fz_stream_t stream) {
+    FZ_REQUIRE(x && (out_f32 || out_bf16), "null pointer");
+    FZ_REQUIRE(dim >= 1, "bad dim");
+    if (n_rows == 0) return FZ_OK;
+    const int warps = 8;
+    normalize_rows_kernel<<<(unsigned)ceil_div<long long>(n_rows, warps), warps * 32, 0, (cudaStream_t)stream>>>(
+        x, n_rows, dim, normalize, out_f32, (__nv_bfloat16*)out_bf16);
+    FZ_LAUNCH_CHECK();
+    return FZ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,347 @@
+// Segmented sort / top-k selection / k-way merge (K5) and the candidate-buffer maintenance used by K1/K2.
+//
+// One CTA per query.  Records are 16-byte `Entry`s (order-preserving score key, tie key, payload) sorted
+// "best first" with a bitonic network: in shared memory when the segment fits (<= 8192 records), otherwise in
+// a global workspace with the short-stride stages done on 4096-record chunks staged through shared memory.
+#include "common.cuh"
+#include "topk_state.cuh"
+
+#include <cstdarg>
+#include <limits>
+
+namespace fz {
+
+// ------------------------------------------------------------------------------------------- error string
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+const char* last_error() { return g_err; }
+
+constexpr int kSortThreads = 1024;
+constexpr int kSmemEntries = 8192;   // 128 KB
+constexpr int kChunk = 4096;         // chunk staged through smem by the large sort
+
+static inline int next_pow2(int n) {
+    int p = 1;
+    while (p < n) p <<= 1;
+    return p;
+}
+
+// compare-exchange stages j = j_hi .. 1 of merge size k on `cnt` records in smem whose global index starts at base
+__device__ __forceinline__ void smem_stages(Entry* sm, int cnt, int base, int k, int j_hi) {
+    for (int j = j_hi; j > 0; j >>= 1) {
+        for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+            int p = i ^ j;
+            if (p > i) {
+                Entry x = sm[i], y = sm[p];
+                bool up = ((base + i) & k) == 0;
+                if (entry_before(y, x) == up) {
+                    sm[i] = y;
+                    sm[p] = x;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// Sort n_pow2 (> kChunk) records in global memory `a`; `sm` holds kChunk records.
+__device__ void bitonic_sort_large(Entry* a, int n_pow2, Entry* sm) {
+    for (int base = 0; base < n_pow2; base += kChunk) {
+        for (int i = threadIdx.x; i < kChunk; i += blockDim.x) sm[i] = a[base + i];
+        __syncthreads();
+        for (int k = 2; k <= kChunk; k <<= 1) smem_stages(sm, kChunk, base, k, k >> 1);
+        for (int i = threadIdx.x; i < kChunk; i += blockDim.x) a[base + i] = sm[i];
+        __syncthreads();
+    }
+    for (int k = 2 * kChunk; k <= n_pow2; k <<= 1) {
+        for (int j = k >> 1; j >= kChunk; j >>= 1) {
+            for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
+                int p = i ^ j;
+                if (p > i) {
+                    Entry x = a[i], y = a[p];
+                    bool up = (i & k) == 0;
+                    if (entry_before(y, x) == up) {
+                        a[i] = y;
+                        a[p] = x;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        for (int base = 0; base < n_pow2; base += kChunk) {
+            for (int i = threadIdx.x; i < kChunk; i += blockDim.x) sm[i] = a[base + i];
+            __syncthreads();
+            smem_stages(sm, kChunk, base, k, kChunk >> 1);
+            for (int i = threadIdx.x; i < kChunk; i += blockDim.x) a[base + i] = sm[i];
+            __syncthreads();
+        }
+    }
+}
+
+__device__ __forceinline__ Entry pad_entry() {
+    Entry e;
+    e.skey = 0;
+    e.tie = 0;
+    e.payload = 0xffffffffu;
+    return e;
+}
+
+// --------------------------------------------------------------------------------- candidate buffers
+template <typename ST>
+__global__ void cand_init_kernel(CandState<ST> st, int n_queries) {
+    int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < n_queries) {
+        st.cnt[q] = 0;
+        st.npos[q] = 0;
+        st.nneg[q] = 0;
+        st.tau[q] = -std::numeric_limits<ST>::infinity();
+        st.status[q] = 0;
+    }
+}
+
+template <typename ST>
+__global__ void __launch_bounds__(kSortThreads) cand_select_kernel(CandState<ST> st, int k, ST margin, int final_out,
+                                                                   long long doc_base, ST* out_scores,
+                                                                   int32_t* out_ids, int32_t* out_n) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Entry* sm = reinterpret_cast<Entry*>(smem_raw);
+    __shared__ int s_keep;
+    const int q = blockIdx.x;
+    const int raw = st.cnt[q];
+    const int n = min(raw, st.cap);
+    if (threadIdx.x == 0) {
+        s_keep = 0;
+        if (raw > st.cap) st.status[q] |= FZ_STATUS_OVERFLOW;
+    }
+    int n_pow2 = 1;
+    while (n_pow2 < n) n_pow2 <<= 1;
+    const size_t off = (size_t)q * st.cap;
+    for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
+        Entry e = pad_entry();
+        if (i < n) {
+            int32_t d = st.id[off + i];
+            e.skey = score_key(st.score[off + i]);
+            e.tie = ~(uint32_t)d;
+            e.payload = (uint32_t)d;
+        }
+        sm[i] = e;
+    }
+    __syncthreads();
+    bitonic_sort_cta(sm, n_pow2);
+
+    int keep = n;
+    ST tau = st.tau[q];
+    if (n >= k) {
+        ST kth;
+        key_score(sm[k - 1].skey, kth);
+        ST t = kth - margin;
+        if (t > tau) tau = t;
+        if (margin == (ST)0) {
+            // Rounds visit docs in ascending id order, so a later doc that merely ties the k-th score loses the
+            // tie (lower id first): keep exactly k and let the scoring kernels emit on score > tau.
+            keep = k;
+        } else {
+            // records are sorted: count those still >= tau
+            const uint64_t tk = score_key(tau);
+            int local = 0;
+            for (int i = threadIdx.x; i < n; i += blockDim.x) local += (sm[i].skey >= tk) ? 1 : 0;
+            local = warp_sum(local);
+            if ((threadIdx.x & 31) == 0 && local) atomicAdd(&s_keep, local);
+            __syncthreads();
+            keep = s_keep;
+        }
+    }
+    for (int i = threadIdx.x; i < keep; i += blockDim.x) {
+        ST s;
+        key_score(sm[i].skey, s);
+        st.score[off + i] = s;
+        st.id[off + i] = (int32_t)sm[i].payload;
+    }
+    if (threadIdx.x == 0) {
+        st.cnt[q] = keep;
+        st.tau[q] = tau;
+    }
+    if (final_out) {
+        const int m = min(keep, k);
+        for (int i = threadIdx.x; i < k; i += blockDim.x) {
+            ST s = -std::numeric_limits<ST>::infinity();
+            int32_t d = -1;
+            if (i < m) {
+                key_score(sm[i].skey, s);
+                d = (int32_t)(doc_base + (long long)sm[i].payload);
+            }
+            out_scores[(size_t)q * k + i] = s;
+            out_ids[(size_t)q * k + i] = d;
+        }
+        if (out_n && threadIdx.x == 0) out_n[q] = m;
+    }
+}
+
+template <typename ST>
+int cand_init(const CandState<ST>& st, int n_queries, cudaStream_t stream) {
+    cand_init_kernel<ST><<<ceil_div(n_queries, 256), 256, 0, stream>>>(st, n_queries);
+    FZ_LAUNCH_CHECK();
+    return FZ_OK;
+}
+
+template <typename ST>
+int cand_select(const CandState<ST>& st, int n_queries, int k, ST margin, bool final_out, int64_t doc_base,
+                ST* out_scores, int32_t* out_ids, int32_t* out_n, cudaStream_t stream) {
+    FZ_REQUIRE(st.cap <= kSmemEntries, "candidate capacity %d exceeds %d", st.cap, kSmemEntries);
+    FZ_REQUIRE(k >= 1 && k <= st.cap, "k=%d must be in [1, cap=%d]", k, st.cap);
+    size_t smem = (size_t)next_pow2(st.cap) * sizeof(Entry);
+    static bool attr_f = false, attr_d = false;
+    bool& done = std::is_same<ST, float>::value ? attr_f : attr_d;
+    if (!done) {
+        FZ_CUDA(cudaFuncSetAttribute(cand_select_kernel<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     kSmemEntries * (int)sizeof(Entry)));
+        done = true;
+    }
+    cand_select_kernel<ST><<<n_queries, kSortThreads, smem, stream>>>(st, k, margin, final_out ? 1 : 0,
+                                                                      (long long)doc_base, out_scores, out_ids, out_n);
+    FZ_LAUNCH_CHECK();
+    return FZ_OK;
+}
+
+template int cand_init<float>(const CandState<float>&, int, cudaStream_t);
+template int cand_init<double>(const CandState<double>&, int, cudaStream_t);
+template int cand_select<float>(const CandState<float>&, int, int, float, bool, int64_t, float*, int32_t*, int32_t*,
+                                cudaStream_t);
+template int cand_select<double>(const CandState<double>&, int, int, double, bool, int64_t, double*, int32_t*,
+                                 int32_t*, cudaStream_t);
+
+// --------------------------------------------------------------------------------- merge / rank rows
+// Segment q gathers `n_src` runs of `run_len` records spaced `src_stride` apart (merge), or one run of
+// n records (rank rows: ids are implicit 0..n-1), sorts them and writes the best k_out.
+template <typename ST>
+__global__ void __launch_bounds__(kSortThreads)
+    segsort_kernel(const ST* __restrict__ scores, const int32_t* __restrict__ ids, int n_src, long long src_stride,
+                   int run_len, long long seg_stride, int k_out, long long id_base, ST* out_scores, int32_t* out_ids,
+                   Entry* gws, int n_pow2) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Entry* sm = reinterpret_cast<Entry*>(smem_raw);
+    const int q = blockIdx.x;
+    const int n = n_src * run_len;
+    const bool in_smem = n_pow2 <= kSmemEntries;
+    Entry* a = in_smem ? sm : gws + (size_t)q * n_pow2;
+    for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
+        Entry e = pad_entry();
+        if (i < n) {
+            int g = i / run_len, r = i - g * run_len;
+            size_t src = (size_t)g * src_stride + (size_t)q * seg_stride + r;
+            int32_t d = ids ? ids[src] : (int32_t)r;
+            if (d >= 0) {
+                e.skey = score_key(scores[src]);
+                e.tie = ~(uint32_t)d;
+                e.payload = (uint32_t)d;
+            }
+        }
+        a[i] = e;
+    }
+    __syncthreads();
+    if (in_smem)
+        bitonic_sort_cta(a, n_pow2);
+    else
+        bitonic_sort_large(a, n_pow2, sm);
+    for (int i = threadIdx.x; i < k_out; i += blockDim.x) {
+        ST s = -std::numeric_limits<ST>::infinity();
+        int32_t d = -1;
+        if (i < n_pow2) {
+            Entry e = a[i];
+            if (e.payload != 0xffffffffu) {
+                key_score(e.skey, s);
+                d = (int32_t)(id_base + (long long)e.payload);
+            }
+        }
+        out_scores[(size_t)q * k_out + i] = s;
+        out_ids[(size_t)q * k_out + i] = d;
+    }
+}
+
+template <typename ST>
+static int launch_segsort(const ST* scores, const int32_t* ids, int n_src, long long src_stride, int run_len,
+                          long long seg_stride, int n_queries, int k_out, long long id_base, ST* out_scores,
+                          int32_t* out_ids, void* ws, size_t ws_bytes, cudaStream_t stream) {
+    long long n = (long long)n_src * run_len;
+    FZ_REQUIRE(n >= 1 && n <= (1ll << 24), "segment length %lld out of range", n);
+    int n_pow2 = next_pow2((int)n);
+    size_t need = n_pow2 > kSmemEntries ? (size_t)n_queries * n_pow2 * sizeof(Entry) : 0;
+    FZ_REQUIRE(ws_bytes >= need, "workspace too small: %zu < %zu", ws_bytes, need);
+    size_t smem = (size_t)(n_pow2 > kSmemEntries ? kChunk : n_pow2) * sizeof(Entry);
+    static bool attr_f = false, attr_d = false;
+    bool& done = std::is_same<ST, float>::value ? attr_f : attr_d;
+    if (!done) {
+        FZ_CUDA(cudaFuncSetAttribute(segsort_kernel<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     kSmemEntries * (int)sizeof(Entry)));
+        done = true;
+    }
+    segsort_kernel<ST><<<n_queries, kSortThreads, smem, stream>>>(scores, ids, n_src, src_stride, run_len, seg_stride,
+                                                                  k_out, id_base, out_scores, out_ids, (Entry*)ws,
+                                                                  n_pow2);
+    FZ_LAUNCH_CHECK();
+    return FZ_OK;
+}
+
+}  // namespace fz
+
+using namespace fz;
+
+extern "C" {
+
+const char* fz_last_error(void) { return fz::last_error(); }
+int fz_abi_version(void) { return FZ_ABI_VERSION; }
+
+size_t fz_merge_topk_workspace_bytes(int n_src, int n_queries, int k_in) {
+    long long n = (long long)n_src * k_in;
+    int p = next_pow2((int)n);
+    return p > kSmemEntries ? (size_t)n_queries * p * sizeof(Entry) : 0;
+}
+
+int fz_merge_topk_f32(const float* scores, const int32_t* ids, int n_src, int n_queries, int k_in, int k_out,
+                      float* out_scores, int32_t* out_ids, void* ws, size_t ws_bytes, fz_stream_t stream) {
+    FZ_REQUIRE(scores && ids && out_scores && out_ids, "null pointer");
+    FZ_REQUIRE(n_src >= 1 && n_queries >= 0 && k_in >= 1 && k_out >= 1, "bad sizes");
+    if (n_queries == 0) return FZ_OK;
+    return launch_segsort<float>(scores, ids, n_src, (long long)n_queries * k_in, k_in, k_in, n_queries, k_out, 0,
+                                 out_scores, out_ids, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int fz_merge_topk_f64(const double* scores, const int32_t* ids, int n_src, int n_queries, int k_in, int k_out,
+                      double* out_scores, int32_t* out_ids, void* ws, size_t ws_bytes, fz_stream_t stream) {
+    FZ_REQUIRE(scores && ids && out_scores && out_ids, "null pointer");
+    FZ_REQUIRE(n_src >= 1 && n_queries >= 0 && k_in >= 1 && k_out >= 1, "bad sizes");
+    if (n_queries == 0) return FZ_OK;
+    return launch_segsort<double>(scores, ids, n_src, (long long)n_queries * k_in, k_in, k_in, n_queries, k_out, 0,
+                                  out_scores, out_ids, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+size_t fz_rank_rows_workspace_bytes(int n_queries, int64_t n_docs) {
+    if (n_docs > (1ll << 24)) return 0;
+    int p = next_pow2((int)n_docs);
+    return p > kSmemEntries ? (size_t)n_queries * p * sizeof(Entry) : 0;
+}
+
+int fz_rank_rows_f32(const float* scores, int n_queries, int64_t n_docs, int k, int64_t doc_base, float* out_scores,
+                     int32_t* out_ids, void* ws, size_t ws_bytes, fz_stream_t stream) {
+    FZ_REQUIRE(scores && out_scores && out_ids, "null pointer");
+    FZ_REQUIRE(n_docs >= 1 && n_docs <= (1ll << 24) && k >= 1, "bad sizes");
+    if (n_queries == 0) return FZ_OK;
+    return launch_segsort<float>(scores, nullptr, 1, 0, (int)n_docs, n_docs, n_queries, k, doc_base, out_scores,
+                                 out_ids, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int fz_rank_rows_f64(const double* scores, int n_queries, int64_t n_docs, int k, int64_t doc_base, double* out_scores,
+                     int32_t* out_ids, void* ws, size_t ws_bytes, fz_stream_t stream) {
+    FZ_REQUIRE(scores && out_scores && out_ids, "null pointer");
+    FZ_REQUIRE(n_docs >= 1 && n_docs <= (1ll << 24) && k >= 1, "bad sizes");
+    if (n_queries == 0) return FZ_OK;
+    return launch_segsort<double>(scores, nullptr, 1, 0, (int)n_docs, n_docs, n_queries, k, doc_base, out_scores,
+                                  out_ids, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,356 @@
+"""Tensor API: torch CUDA tensors in, torch CUDA tensors out, every op one or more calls into the C ABI.
+
+torch is plumbing here (device memory, the current stream); the arithmetic is in libfusion_b200.so.  This is
+the level ``bench.py`` measures; the drop-in adapters in ``fusion_b200.retrievers`` wrap it into the
+reference's list-of-dict shapes.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+from ._lib import FZ_STATUS_NEED_NEG, FZ_STATUS_OVERFLOW, FusionB200Error, check
+
+DEFAULT_CAP = 8192
+DEFAULT_GROWTH = 4
+
+
+def _stream(t: torch.Tensor) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _ptr(t: torch.Tensor | None) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _req(t: torch.Tensor, dtype: torch.dtype, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise FusionB200Error(f"{name} must be a CUDA tensor (fusion_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise FusionB200Error(f"{name} must be {dtype}, got {t.dtype}")
+    return t.contiguous()
+
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+# ----------------------------------------------------------------------------------------------- K5
+def merge_topk(scores: torch.Tensor, ids: torch.Tensor, k_out: int):
+    """k-way merge of ``n_src`` top-k lists: scores/ids [n_src, Q, k_in] -> ([Q, k_out], [Q, k_out]),
+    best first (score desc, ties by lower id), padded with (-inf, -1); entries with id < 0 are ignored."""
+    lib = _lib.load()
+    f64 = scores.dtype == torch.float64
+    scores = _req(scores, torch.float64 if f64 else torch.float32, "scores")
+    ids = _req(ids, torch.int32, "ids")
+    g, q, k_in = scores.shape
+    out_s = torch.empty((q, k_out), dtype=scores.dtype, device=scores.device)
+    out_i = torch.empty((q, k_out), dtype=torch.int32, device=scores.device)
+    ws = _ws(lib.fz_merge_topk_workspace_bytes(g, q, k_in), scores.device)
+    fn = lib.fz_merge_topk_f64 if f64 else lib.fz_merge_topk_f32
+    check(fn(_ptr(scores), _ptr(ids), g, q, k_in, k_out, _ptr(out_s), _ptr(out_i), _ptr(ws), ws.numel(),
+             _stream(scores)), "fz_merge_topk")
+    return out_s, out_i
+
+
+def rank_rows(scores: torch.Tensor, k: int, doc_base: int = 0, max_ws_bytes: int = 1 << 30):
+    """Rank every column of each row: scores [Q, N] -> top-k (score desc, ties by lower index)."""
+    lib = _lib.load()
+    f64 = scores.dtype == torch.float64
+    scores = _req(scores, torch.float64 if f64 else torch.float32, "scores")
+    q, n = scores.shape
+    out_s = torch.empty((q, k), dtype=scores.dtype, device=scores.device)
+    out_i = torch.empty((q, k), dtype=torch.int32, device=scores.device)
+    fn = lib.fz_rank_rows_f64 if f64 else lib.fz_rank_rows_f32
+    per_q = max(1, lib.fz_rank_rows_workspace_bytes(1, n))
+    step = max(1, min(q, max_ws_bytes // per_q))
+    for lo in range(0, q, step):
+        hi = min(q, lo + step)
+        ws = _ws(lib.fz_rank_rows_workspace_bytes(hi - lo, n), scores.device)
+        check(fn(_ptr(scores[lo:hi]), hi - lo, n, k, doc_base, _ptr(out_s[lo:hi]), _ptr(out_i[lo:hi]), _ptr(ws),
+                 ws.numel(), _stream(scores)), "fz_rank_rows")
+    return out_s, out_i
+
+
+# ----------------------------------------------------------------------------------------------- K4
+def fuse(lists, method: str, normalization: str | None = None, weights=None, distributions=None,
+         out_stride: int | None = None, max_ws_bytes: int = 2 << 30):
+    """Fuse ``S`` ranked-list systems.
+
+    lists: sequence of (ids int32 [Q, n_s], scores f32|f64 [Q, n_s], lens int32 [Q] | None), rank order.
+    -> (ids int32 [Q, U], scores f64 [Q, U], lens int32 [Q]); U = out_stride or sum(n_s).  Rows are the union of
+    the lists, fused score descending, ties by first insertion; padded with (-1, -inf).
+    """
+    lib = _lib.load()
+    if method not in _lib.FUSE_METHODS:
+        raise FusionB200Error(f"unknown fusion method {method!r}")
+    if method == "nsf" and normalization not in _lib.FUSE_NORMS:
+        raise FusionB200Error(f"unknown normalization {normalization!r}")
+    s = len(lists)
+    dev = lists[0][0].device
+    q = lists[0][0].shape[0]
+    ids_t, sc_t, len_t, strides, is64 = [], [], [], [], []
+    for i, (ids, sc, lens) in enumerate(lists):
+        f64 = sc.dtype == torch.float64
+        ids_t.append(_req(ids, torch.int32, f"ids[{i}]"))
+        sc_t.append(_req(sc, torch.float64 if f64 else torch.float32, f"scores[{i}]"))
+        len_t.append(None if lens is None else _req(lens, torch.int32, f"lens[{i}]"))
+        if ids.shape != sc.shape or ids.shape[0] != q:
+            raise FusionB200Error("ranked lists of different systems cover different numbers of queries")
+        strides.append(ids.shape[1])
+        is64.append(1 if f64 else 0)
+    total = sum(strides)
+    u = out_stride or total
+    norm_code = _lib.FUSE_NORMS[normalization] if method == "nsf" else 0
+    need_distr = method == "nsf" and norm_code in (4, 5)
+    distr_t = []
+    if need_distr:
+        if distributions is None or len(distributions) != s:
+            raise FusionB200Error("percentile normalisation needs one distribution per system")
+        for d in distributions:
+            d = torch.as_tensor(d).to(device=dev, dtype=torch.float32).contiguous()
+            if d.numel() > 1 and bool((d[1:] < d[:-1]).any()):
+                raise FusionB200Error("percentile distributions must be ascending")
+            distr_t.append(d)
+    arr_p = C.c_void_p * s
+    arr_i = C.c_int32 * s
+    arr_d = C.c_double * s
+    w = [1.0] * s if weights is None else [float(x) for x in weights]
+    out_ids = torch.empty((q, u), dtype=torch.int32, device=dev)
+    out_sc = torch.empty((q, u), dtype=torch.float64, device=dev)
+    out_len = torch.empty((q,), dtype=torch.int32, device=dev)
+    stride_arr = arr_i(*strides)
+    per_q = lib.fz_fuse_workspace_bytes(s, 1, stride_arr)
+    step = q if per_q == 0 else max(1, min(q, max_ws_bytes // per_q))
+    for lo in range(0, q, step):
+        hi = min(q, lo + step)
+        ws = _ws(lib.fz_fuse_workspace_bytes(s, hi - lo, stride_arr), dev)
+        check(lib.fz_fuse(
+            arr_p(*[t[lo:hi].data_ptr() for t in ids_t]), arr_p(*[t[lo:hi].data_ptr() for t in sc_t]),
+            arr_p(*[0 if t is None else t[lo:hi].data_ptr() for t in len_t]), arr_i(*is64), stride_arr, s, hi - lo,
+            _lib.FUSE_METHODS[method], norm_code, arr_d(*w),
+            arr_p(*[d.data_ptr() for d in distr_t]) if need_distr else None,
+            arr_i(*[d.numel() for d in distr_t]) if need_distr else None,
+            _ptr(out_ids[lo:hi]), _ptr(out_sc[lo:hi]), _ptr(out_len[lo:hi]), u, _ptr(ws), ws.numel(), _stream(out_ids)),
+            "fz_fuse")
+    return out_ids, out_sc, out_len
+
+
+# ----------------------------------------------------------------------------------------------- K2
+@dataclass
+class PostingsView:
+    """Device CSR postings + tile table, as the C struct wants them (see fusion_b200.index)."""
+    term_ptr: torch.Tensor       # int64 [V+1]
+    post_doc: torch.Tensor       # int32 [nnz]
+    post_val: torch.Tensor       # float64 | float32 [nnz]
+    long_row: torch.Tensor       # int32 [V]
+    long_tile_off: torch.Tensor  # uint32 viewed as int32 [n_long, n_tiles+1]
+    n_docs: int
+    tile_docs: int
+
+    @property
+    def n_tiles(self) -> int:
+        return (self.n_docs + self.tile_docs - 1) // self.tile_docs
+
+    def c_struct(self) -> _lib.Postings:
+        return _lib.Postings(self.term_ptr.data_ptr(), self.post_doc.data_ptr(), self.post_val.data_ptr(),
+                             self.long_row.data_ptr(), self.long_tile_off.data_ptr() if self.long_tile_off.numel() else 0,
+                             self.term_ptr.numel() - 1, self.long_tile_off.shape[0], self.n_docs, self.tile_docs,
+                             self.n_tiles)
+
+
+def _sparse_topk_once(pv: PostingsView, q_ptr, q_term, q_weight, k, doc_base, cap, growth, sign_mode):
+    lib = _lib.load()
+    f64 = pv.post_val.dtype == torch.float64
+    dev = pv.post_doc.device
+    nq = q_ptr.numel() - 1
+    out_s = torch.empty((nq, k), dtype=pv.post_val.dtype, device=dev)
+    out_i = torch.empty((nq, k), dtype=torch.int32, device=dev)
+    status = torch.empty((nq,), dtype=torch.int32, device=dev)
+    ws = _ws(lib.fz_sparse_topk_workspace_bytes(nq, k, cap, 1 if f64 else 0), dev)
+    st = pv.c_struct()
+    if f64:
+        check(lib.fz_sparse_topk_f64(C.byref(st), _ptr(q_ptr), _ptr(q_term), nq, k, doc_base, cap, growth, sign_mode,
+                                     _ptr(out_s), _ptr(out_i), _ptr(status), _ptr(ws), ws.numel(), _stream(out_s)),
+              "fz_sparse_topk_f64")
+    else:
+        check(lib.fz_sparse_topk_f32(C.byref(st), _ptr(q_ptr), _ptr(q_term), _ptr(q_weight), nq, k, doc_base, cap,
+                                     growth, sign_mode, _ptr(out_s), _ptr(out_i), _ptr(status), _ptr(ws), ws.numel(),
+                                     _stream(out_s)), "fz_sparse_topk_f32")
+    return out_s, out_i, status
+
+
+def _subset_queries(q_ptr, q_term, q_weight, sel):
+    """CSR rows ``sel`` of the query matrix (host-side index arithmetic on a handful of flagged queries)."""
+    ptr = q_ptr.cpu()
+    sel_l = sel.cpu().tolist()
+    lens = [int(ptr[i + 1] - ptr[i]) for i in sel_l]
+    idx = torch.cat([torch.arange(int(ptr[i]), int(ptr[i + 1])) for i in sel_l]) if sum(lens) else torch.zeros(0, dtype=torch.long)
+    new_ptr = torch.zeros(len(sel_l) + 1, dtype=torch.int32)
+    new_ptr[1:] = torch.tensor(lens, dtype=torch.int32).cumsum(0)
+    idx = idx.to(q_term.device)
+    return (new_ptr.to(q_term.device), q_term[idx].contiguous(),
+            None if q_weight is None else q_weight[idx].contiguous())
+
+
+def sparse_topk(pv: PostingsView, q_ptr, q_term, q_weight, k: int, doc_base: int = 0, cap: int = DEFAULT_CAP,
+                growth: int = DEFAULT_GROWTH):
+    """Top-k of sum_t w_qt * val[t, d] over an inverted index -> (scores [Q,k], ids [Q,k] int32).
+
+    Order: score desc, ties by lower doc id; docs that match nothing score 0 and fill up in doc-id order; negative
+    scores (BM25 idf < 0 for df > N/2) rank after the zeros - exactly the reference's `sorted(..., reverse=True)`
+    over every document (src/retrievers/bm25.py:100-106)."""
+    q_ptr = _req(q_ptr, torch.int32, "q_ptr")
+    q_term = _req(q_term, torch.int32, "q_term")
+    if q_weight is not None:
+        q_weight = _req(q_weight, torch.float32, "q_weight")
+    k_eff = min(k, pv.n_docs)
+    cap = max(cap, 2 * k_eff)
+    out_s, out_i, status = _sparse_topk_once(pv, q_ptr, q_term, q_weight, k_eff, doc_base, cap, growth, +1)
+    st = status.cpu()
+    over = (st & FZ_STATUS_OVERFLOW) != 0
+    if bool(over.any()):            # rare: redo those queries with rounds that cannot overflow
+        sel = torch.nonzero(over).flatten()
+        p2, t2, w2 = _subset_queries(q_ptr, q_term, q_weight, sel)
+        s2, i2, st2 = _sparse_topk_once(pv, p2, t2, w2, k_eff, doc_base, cap, 1, +1)
+        if bool(((st2.cpu() & FZ_STATUS_OVERFLOW) != 0).any()):
+            raise FusionB200Error("sparse top-k overflowed even with conservative rounds")
+        seld = sel.to(out_s.device)
+        out_s[seld], out_i[seld] = s2, i2
+        st[sel] = st2.cpu()
+    need_neg = (st & FZ_STATUS_NEED_NEG) != 0
+    if bool(need_neg.any()):        # positives + zero-score docs < k: the tail is the best of the negative scores
+        sel = torch.nonzero(need_neg).flatten()
+        p2, t2, w2 = _subset_queries(q_ptr, q_term, q_weight, sel)
+        s2, i2, st2 = _sparse_topk_once(pv, p2, t2, w2, k_eff, doc_base, cap, 1, -1)
+        for j, qi in enumerate(sel.tolist()):
+            have = int((out_i[qi] >= 0).sum())
+            take = k_eff - have
+            out_s[qi, have:] = s2[j, :take]
+            out_i[qi, have:] = i2[j, :take]
+    return out_s, out_i
+
+
+def sparse_scores(pv: PostingsView, q_ptr, q_term, q_weight=None):
+    """Score of every document for every query: [Q, n_docs] (fp64 for lexical impacts, fp32 for SPLADE weights)."""
+    lib = _lib.load()
+    q_ptr = _req(q_ptr, torch.int32, "q_ptr")
+    q_term = _req(q_term, torch.int32, "q_term")
+    nq = q_ptr.numel() - 1
+    f64 = pv.post_val.dtype == torch.float64
+    out = torch.empty((nq, pv.n_docs), dtype=pv.post_val.dtype, device=pv.post_doc.device)
+    st = pv.c_struct()
+    if f64:
+        check(lib.fz_sparse_scores_f64(C.byref(st), _ptr(q_ptr), _ptr(q_term), nq, _ptr(out), _stream(out)),
+              "fz_sparse_scores_f64")
+    else:
+        if q_weight is not None:
+            q_weight = _req(q_weight, torch.float32, "q_weight")
+        check(lib.fz_sparse_scores_f32(C.byref(st), _ptr(q_ptr), _ptr(q_term), _ptr(q_weight), nq, _ptr(out),
+                                       _stream(out)), "fz_sparse_scores_f32")
+    return out
+
+
+def lexical_impacts(term_ptr, post_doc, post_tf, doc_len, idf, avgdl: float, k1: float, b: float, variant: int):
+    lib = _lib.load()
+    out = torch.empty(post_doc.numel(), dtype=torch.float64, device=post_doc.device)
+    check(lib.fz_lexical_impacts(_ptr(_req(term_ptr, torch.int64, "term_ptr")), _ptr(_req(post_doc, torch.int32, "post_doc")),
+                                 _ptr(_req(post_tf, torch.int32, "post_tf")),
+                                 _ptr(None if doc_len is None else _req(doc_len, torch.int32, "doc_len")),
+                                 _ptr(_req(idf, torch.float64, "idf")), term_ptr.numel() - 1, post_doc.numel(),
+                                 float(avgdl), float(k1), float(b), variant, _ptr(out), _stream(out)), "fz_lexical_impacts")
+    return out
+
+
+def long_tile_offsets(term_ptr, post_doc, long_terms, tile_docs: int, n_tiles: int):
+    lib = _lib.load()
+    n_long = long_terms.numel()
+    out = torch.zeros((n_long, n_tiles + 1), dtype=torch.int32, device=post_doc.device)   # uint32 payload
+    if n_long:
+        check(lib.fz_long_tile_offsets(_ptr(term_ptr), _ptr(post_doc), _ptr(_req(long_terms, torch.int32, "long_terms")),
+                                       n_long, tile_docs, n_tiles, _ptr(out), _stream(out)), "fz_long_tile_offsets")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- K1
+def normalize_rows(x: torch.Tensor, normalize: bool = True, want_f32: bool = True, want_bf16: bool = True):
+    """rows / max(||row||, 1e-12) -> (fp32 copy | None, bf16 copy | None)."""
+    lib = _lib.load()
+    x = _req(x, torch.float32, "x")
+    n, d = x.shape
+    o32 = torch.empty_like(x) if want_f32 else None
+    o16 = torch.empty((n, d), dtype=torch.bfloat16, device=x.device) if want_bf16 else None
+    check(lib.fz_normalize_rows(_ptr(x), n, d, 1 if normalize else 0, _ptr(o32), _ptr(o16), _stream(x)),
+          "fz_normalize_rows")
+    return o32, o16
+
+
+def dense_topk(q_bf16, d_bf16, q_f32, d_f32, k: int, margin: float = 0.0, doc_base: int = 0,
+               cap: int = DEFAULT_CAP, growth: int = DEFAULT_GROWTH):
+    """Exhaustive inner-product top-k (tcgen05 GEMM with the threshold filter in its epilogue).
+
+    q_bf16 [Q, d], d_bf16 [N, d] are the tensor-core operands; with q_f32 / d_f32 the survivors within ``margin`` of
+    the running k-th bf16 score are rescored in fp32 (exact mode).  -> (scores f32 [Q,k], ids int32 [Q,k])."""
+    lib = _lib.load()
+    q_bf16 = _req(q_bf16, torch.bfloat16, "q_bf16")
+    d_bf16 = _req(d_bf16, torch.bfloat16, "d_bf16")
+    exact = d_f32 is not None
+    if exact:
+        q_f32 = _req(q_f32, torch.float32, "q_f32")
+        d_f32 = _req(d_f32, torch.float32, "d_f32")
+    nq, dim = q_bf16.shape
+    n = d_bf16.shape[0]
+    k_eff = min(k, n)
+    cap = max(cap, 2 * k_eff)
+    out_s = torch.empty((nq, k_eff), dtype=torch.float32, device=q_bf16.device)
+    out_i = torch.empty((nq, k_eff), dtype=torch.int32, device=q_bf16.device)
+    status = torch.empty((nq,), dtype=torch.int32, device=q_bf16.device)
+    ws = _ws(lib.fz_dense_topk_workspace_bytes(nq, k_eff, cap), q_bf16.device)
+
+    def run(g):
+        check(lib.fz_dense_topk(_ptr(q_bf16), _ptr(d_bf16), _ptr(q_f32 if exact else None),
+                                _ptr(d_f32 if exact else None), nq, n, dim, k_eff, float(margin), doc_base, cap, g,
+                                _ptr(out_s), _ptr(out_i), _ptr(status), _ptr(ws), ws.numel(), _stream(out_s)),
+              "fz_dense_topk")
+
+    run(growth)
+    if bool(((status & FZ_STATUS_OVERFLOW) != 0).any()):
+        if margin > 0:
+            raise FusionB200Error("dense top-k candidate buffer overflowed: lower `margin` or raise `cap`")
+        run(1)      # conservative rounds never overflow when margin == 0
+    return out_s, out_i
+
+
+def dense_scores(q_f32, d_f32):
+    """Exact fp32 [Q, N] score matrix on CUDA cores (full-ranking mode on small corpora)."""
+    lib = _lib.load()
+    q_f32 = _req(q_f32, torch.float32, "q_f32")
+    d_f32 = _req(d_f32, torch.float32, "d_f32")
+    out = torch.empty((q_f32.shape[0], d_f32.shape[0]), dtype=torch.float32, device=q_f32.device)
+    check(lib.fz_dense_scores_f32(_ptr(q_f32), _ptr(d_f32), q_f32.shape[0], d_f32.shape[0], q_f32.shape[1], _ptr(out),
+                                  _stream(out)), "fz_dense_scores_f32")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- K3
+def maxsim(q_tok_bf16, tok_ptr, tok_emb_bf16, cand_ids, doc_base: int = 0):
+    """ColBERT MaxSim of every (query, candidate) pair -> fp32 [Q, C].
+
+    q_tok_bf16 [Q, Lq, 128], tok_ptr int64 [N+1], tok_emb_bf16 [T, 128], cand_ids int32 [Q, C] (global ids;
+    candidates outside [doc_base, doc_base+N) are skipped and score 0)."""
+    lib = _lib.load()
+    q_tok_bf16 = _req(q_tok_bf16, torch.bfloat16, "q_tok")
+    tok_emb_bf16 = _req(tok_emb_bf16, torch.bfloat16, "tok_emb")
+    tok_ptr = _req(tok_ptr, torch.int64, "tok_ptr")
+    cand_ids = _req(cand_ids, torch.int32, "cand_ids")
+    nq, lq, dim = q_tok_bf16.shape
+    if dim != 128 or tok_emb_bf16.shape[1] != 128:
+        raise FusionB200Error("maxsim needs 128-dimensional token embeddings")
+    out = torch.empty(cand_ids.shape, dtype=torch.float32, device=cand_ids.device)
+    check(lib.fz_maxsim_bf16(_ptr(q_tok_bf16), lq, _ptr(cand_ids), _ptr(tok_ptr), _ptr(tok_emb_bf16),
+                             tok_emb_bf16.shape[0], tok_ptr.numel() - 1, doc_base, nq, cand_ids.shape[1], _ptr(out),
+                             _stream(out)), "fz_maxsim_bf16")
+    return out

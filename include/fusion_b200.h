@@ -1,0 +1,181 @@
+/* fusion_b200 — C ABI of the B200 (sm_100a) retrieval-scoring + rank-fusion library.
+ *
+ * The reference (maastrichtlawtech/fusion) is pure Python and has no FFI layer: its boundary is the Python
+ * call signatures listed per entry point below.  The Python package `fusion_b200` keeps those signatures and
+ * calls these functions through ctypes; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - extern "C", plain pointers + sizes.  Every pointer is DEVICE memory unless the name ends in `_h`.
+ *   - The caller owns all memory (inputs, outputs, workspace); `*_workspace_bytes` sizes the scratch.
+ *   - Functions enqueue work on `stream` and return; they never synchronise, allocate or throw.
+ *   - Return 0 on success, FZ_ERR_* (< 0) otherwise; `fz_last_error()` holds the message (thread local).
+ *   - Document ids are int32, global = doc_base + row inside the shard.  Padding slots hold id -1.
+ */
+#ifndef FUSION_B200_H
+#define FUSION_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FZ_OK 0
+#define FZ_ERR_ARG (-1)
+#define FZ_ERR_CUDA (-2)
+#define FZ_ERR_UNSUPPORTED (-3)
+
+#define FZ_ABI_VERSION 1
+
+typedef void* fz_stream_t; /* cudaStream_t */
+
+const char* fz_last_error(void);
+int fz_abi_version(void);
+
+/* per-query status bits written by the top-k entry points */
+#define FZ_STATUS_OVERFLOW 1  /* candidate buffer overflowed: result for this query is NOT valid, re-run with growth=1 */
+#define FZ_STATUS_NEED_ZERO 2 /* fewer than k positive-score docs: zero-score docs were appended in doc-id order */
+#define FZ_STATUS_NEED_NEG 4  /* positives + zero-score docs < k: negative-score docs are missing from the tail */
+
+/* ------------------------------------------------------------------------------------------------------------
+ * K5  k-way merge of per-shard / per-chunk top-k lists.
+ * Replaces the Python heapq merges in src/retrievers/splade/base.py:235-243 and
+ * src/utils/sentence_transformers.py:358-364, and is the merge step after the multi-GPU all-gather.
+ *   scores/ids: [n_src, n_queries, k_in]  (entries with id < 0 are ignored)
+ *   out:        [n_queries, k_out], best first (score desc, ties by lower id), padded with (-inf, -1)
+ * ---------------------------------------------------------------------------------------------------------- */
+size_t fz_merge_topk_workspace_bytes(int n_src, int n_queries, int k_in);
+int fz_merge_topk_f32(const float* scores, const int32_t* ids, int n_src, int n_queries, int k_in, int k_out,
+                      float* out_scores, int32_t* out_ids, void* ws, size_t ws_bytes, fz_stream_t stream);
+int fz_merge_topk_f64(const double* scores, const int32_t* ids, int n_src, int n_queries, int k_in, int k_out,
+                      double* out_scores, int32_t* out_ids, void* ws, size_t ws_bytes, fz_stream_t stream);
+
+/* Full ranking of dense score rows (the reference's `top_k = len(documents)` mode, src/retrievers/hybrid.py:74,103):
+ *   scores [n_queries, n_docs] -> out [n_queries, k] sorted by score desc, ties by lower doc index (stable sort,
+ *   src/retrievers/bm25.py:105). */
+size_t fz_rank_rows_workspace_bytes(int n_queries, int64_t n_docs);
+int fz_rank_rows_f32(const float* scores, int n_queries, int64_t n_docs, int k, int64_t doc_base, float* out_scores,
+                     int32_t* out_ids, void* ws, size_t ws_bytes, fz_stream_t stream);
+int fz_rank_rows_f64(const double* scores, int n_queries, int64_t n_docs, int k, int64_t doc_base, double* out_scores,
+                     int32_t* out_ids, void* ws, size_t ws_bytes, fz_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * K4  rank fusion.  Replaces Aggregator.fuse / convert2dict / transform_scores / weight_scores /
+ * aggregate_scores, src/retrievers/hybrid.py:170-307.
+ *   ids_h[s], scores_h[s]: host arrays of n_sys DEVICE pointers, each [n_queries, list_stride[s]]
+ *   lens_h[s]: device int32 [n_queries] (NULL => every list has list_stride[s] entries)
+ *   score_is_f64_h[s]: 1 if scores_h[s] points at doubles, 0 for floats
+ *   method: FZ_FUSE_*; normalization: FZ_NORM_* (nsf only); weights_h: host doubles [n_sys] (nsf only)
+ *   distr_h[s]: device float32 percentile distribution of length distr_len_h[s], ASCENDING (percentile / NCE only)
+ *   out_ids [n_queries, out_stride], out_scores (double) [n_queries, out_stride], out_len [n_queries]:
+ *       the union of the lists, fused score descending, ties by first insertion (system order, then rank)
+ * ---------------------------------------------------------------------------------------------------------- */
+#define FZ_FUSE_BCF 0
+#define FZ_FUSE_RRF 1
+#define FZ_FUSE_NSF 2
+#define FZ_NORM_NONE 0
+#define FZ_NORM_MINMAX 1
+#define FZ_NORM_ZSCORE 2
+#define FZ_NORM_ARCTAN 3
+#define FZ_NORM_PERCENTILE 4
+#define FZ_NORM_NCE 5
+#define FZ_NORM_IDENTITY_F32 6 /* scores taken as fp32, weighted and summed in fp32 (np.float32 inputs to aggregate_scores) */
+#define FZ_FUSE_MAX_SYSTEMS 8
+
+size_t fz_fuse_workspace_bytes(int n_sys, int n_queries, const int32_t* list_stride_h);
+int fz_fuse(const int32_t* const* ids_h, const void* const* scores_h, const int32_t* const* lens_h,
+            const int32_t* score_is_f64_h, const int32_t* list_stride_h, int n_sys, int n_queries, int method,
+            int normalization, const double* weights_h, const float* const* distr_h, const int32_t* distr_len_h,
+            int32_t* out_ids, double* out_scores, int32_t* out_len, int out_stride, void* ws, size_t ws_bytes,
+            fz_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * K2  sparse scoring over a term-major CSR inverted index, document range tiled for shared-memory accumulators.
+ * Replaces TFIDF/BM25/AtireBM25.score + .search (src/retrievers/bm25.py:100-115,149-156) and, for SPLADE,
+ * the dense [Q,V]x[V,N] cosine of src/retrievers/hybrid.py:101-103 / splade/base.py:186-197.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct fz_postings {
+    const int64_t* term_ptr;       /* [n_terms + 1] */
+    const int32_t* post_doc;       /* [nnz] local doc row, ascending inside a term */
+    const void* post_val;          /* [nnz] double impacts (lexical) or float weights (SPLADE) */
+    const int32_t* long_row;       /* [n_terms] row into long_tile_off, or -1 for short posting lists */
+    const uint32_t* long_tile_off; /* [n_long, n_tiles + 1] offsets (relative to term_ptr[t]) of each doc tile */
+    int32_t n_terms;
+    int32_t n_long;
+    int64_t n_docs;
+    int32_t tile_docs; /* docs per tile (multiple of 256, accumulators must fit shared memory) */
+    int32_t n_tiles;
+} fz_postings_t;
+
+#define FZ_LEX_TFIDF 0
+#define FZ_LEX_BM25 1 /* also ATIRE: only the idf table differs */
+
+/* per-posting fp64 impact, evaluated with the reference's operation order and no FMA contraction:
+ *   TF-IDF: tf * idf                                           (bm25.py:114)
+ *   BM25:   idf * (tf * (k1 + 1)) / (tf + k1 * (1 - b + b * dl / avgdl))   (bm25.py:155) */
+int fz_lexical_impacts(const int64_t* term_ptr, const int32_t* post_doc, const int32_t* post_tf, const int32_t* doc_len,
+                       const double* idf, int32_t n_terms, int64_t nnz, double avgdl, double k1, double b, int variant,
+                       double* out_impact, fz_stream_t stream);
+
+/* offsets of every doc tile inside the long posting lists (index build helper) */
+int fz_long_tile_offsets(const int64_t* term_ptr, const int32_t* post_doc, const int32_t* long_terms, int32_t n_long,
+                         int32_t tile_docs, int32_t n_tiles, uint32_t* out_long_tile_off, fz_stream_t stream);
+
+/* top-k: out [n_queries, k] (score desc, ties by lower doc id); zero-score docs fill up in doc-id order.
+ *   q_ptr [n_queries+1], q_term [nq] (term ids in query-token order, duplicates kept, -1 = out of vocabulary),
+ *   q_weight [nq] float (f32 variant only; NULL => 1)
+ *   growth: >= 2 geometric round growth (fast path), 1 = conservative rounds that can never overflow
+ *   out_status [n_queries]: FZ_STATUS_* bits                                                              */
+size_t fz_sparse_topk_workspace_bytes(int n_queries, int k, int cap, int is_f64);
+int fz_sparse_topk_f64(const fz_postings_t* index, const int32_t* q_ptr, const int32_t* q_term, int n_queries, int k,
+                       int64_t doc_base, int cap, int growth, int sign_mode, double* out_scores, int32_t* out_ids,
+                       int32_t* out_status, void* ws, size_t ws_bytes, fz_stream_t stream);
+int fz_sparse_topk_f32(const fz_postings_t* index, const int32_t* q_ptr, const int32_t* q_term, const float* q_weight,
+                       int n_queries, int k, int64_t doc_base, int cap, int growth, int sign_mode, float* out_scores,
+                       int32_t* out_ids, int32_t* out_status, void* ws, size_t ws_bytes, fz_stream_t stream);
+/* every document's score: out [n_queries, n_docs] (full-ranking mode and tests) */
+int fz_sparse_scores_f64(const fz_postings_t* index, const int32_t* q_ptr, const int32_t* q_term, int n_queries,
+                         double* out_scores, fz_stream_t stream);
+int fz_sparse_scores_f32(const fz_postings_t* index, const int32_t* q_ptr, const int32_t* q_term, const float* q_weight,
+                         int n_queries, float* out_scores, fz_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * K1  dense exhaustive inner-product scoring with top-k fused into the tcgen05 GEMM epilogue.
+ * Replaces sentence_transformers.util.semantic_search (src/retrievers/hybrid.py:103), BaseModel.search /
+ * compute_batchwise_similarity (src/retrievers/splade/base.py:186-251) and the scoring loop of
+ * InformationRetrievalEvaluatorCustom.compute_metrices (src/utils/sentence_transformers.py:334-364).
+ * Inputs are already L2-normalised for cos_sim (fz_normalize_rows).
+ *   q_bf16 [n_queries, dim], d_bf16 [n_docs, dim]: tensor-core operands (dim % 64 == 0)
+ *   q_f32 / d_f32: fp32 originals for exact rescoring of the survivors, or NULL for the bf16 throughput mode
+ *   margin: candidates within `margin` below the running k-th bf16 score are kept for rescoring
+ * ---------------------------------------------------------------------------------------------------------- */
+size_t fz_dense_topk_workspace_bytes(int n_queries, int k, int cap);
+int fz_dense_topk(const void* q_bf16, const void* d_bf16, const float* q_f32, const float* d_f32, int n_queries,
+                  int64_t n_docs, int dim, int k, float margin, int64_t doc_base, int cap, int growth,
+                  float* out_scores, int32_t* out_ids, int32_t* out_status, void* ws, size_t ws_bytes,
+                  fz_stream_t stream);
+/* exact fp32 scores of every (query, doc) pair on CUDA cores: out [n_queries, n_docs] (full-ranking mode) */
+int fz_dense_scores_f32(const float* q_f32, const float* d_f32, int n_queries, int64_t n_docs, int dim,
+                        float* out_scores, fz_stream_t stream);
+/* rows / max(||row||, 1e-12) (torch.nn.functional.normalize, base.py:195-196); either output may be NULL;
+ * normalize == 0 only converts. */
+int fz_normalize_rows(const float* x, int64_t n_rows, int dim, int normalize, float* out_f32, void* out_bf16,
+                      fz_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * K3  ColBERT MaxSim over candidate token tiles: S(q, d) = sum_i max_j <Q_i, D_j>  (tcgen05, bf16 in, fp32 acc).
+ * Replaces colbert-ai `colbert_score` reached through CustomSearcher.search_all (src/utils/colbert_ir.py:245-255)
+ * and Ranker.multi_vector_search (src/retrievers/hybrid.py:109-137).
+ *   q_tok [n_queries * lq, 128] bf16, tok_ptr [n_docs + 1] int64, tok_emb [n_tokens, 128] bf16,
+ *   cand_ids [n_queries, n_cand] global ids (ids outside [doc_base, doc_base + n_docs) are skipped, score 0)
+ *   out_scores [n_queries, n_cand] fp32
+ * ---------------------------------------------------------------------------------------------------------- */
+int fz_maxsim_bf16(const void* q_tok, int lq, const int32_t* cand_ids, const int64_t* tok_ptr, const void* tok_emb,
+                   int64_t n_tokens, int64_t n_docs, int64_t doc_base, int n_queries, int n_cand, float* out_scores,
+                   fz_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FUSION_B200_H */
