@@ -34,6 +34,8 @@ _p, _i, _i64, _sz, _f, _d = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_floa
 SIGNATURES = {
     "fz_last_error": (C.c_char_p, []),
     "fz_abi_version": (_i, []),
+    "fz_profile_enable": (_i, [_i]),
+    "fz_profile_summary": (_i, [C.c_char_p, _sz]),
     "fz_merge_topk_workspace_bytes": (_sz, [_i, _i, _i]),
     "fz_merge_topk_f32": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p, _sz, _p]),
     "fz_merge_topk_f64": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p, _sz, _p]),

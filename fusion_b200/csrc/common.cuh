@@ -36,6 +36,16 @@ void set_error(const char* fmt, ...);
 
 #define FZ_LAUNCH_CHECK() FZ_CUDA(cudaGetLastError())
 
+// Optional per-kernel timing (fz_profile_enable): CUDA events recorded on the launching stream around each
+// instrumented launch; fz_profile_summary synchronises them and reports count / total ms per kernel name.
+void prof_begin(const char* name, cudaStream_t stream);
+void prof_end(cudaStream_t stream);
+struct ProfScope {
+    cudaStream_t s;
+    ProfScope(const char* name, cudaStream_t stream) : s(stream) { prof_begin(name, stream); }
+    ~ProfScope() { prof_end(s); }
+};
+
 inline int num_sms() {
     static int n = 0;
     if (n == 0) {

@@ -364,7 +364,10 @@ int fz_dense_topk(const void* q_bf16, const void* d_bf16, const float* q_f32, co
         G.n_tiles = (int)ceil_div<long long>(hi - lo, kBN);
         const long long tiles = (long long)G.m_tiles * G.n_tiles;
         const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-        dense_filter_kernel<<<grid, kGemmThreads, kGemmSmem, stream>>>(tmap_q, tmap_d, G);
+        {
+            ProfScope prof("dense_filter_gemm", stream);
+            dense_filter_kernel<<<grid, kGemmThreads, kGemmSmem, stream>>>(tmap_q, tmap_d, G);
+        }
         FZ_LAUNCH_CHECK();
         const bool last = hi >= n_docs;
         rc = cand_select<float>(G.st, n_queries, k, margin, last && !exact, doc_base, out_scores, out_ids, nullptr, stream);
@@ -375,7 +378,10 @@ int fz_dense_topk(const void* q_bf16, const void* d_bf16, const float* q_f32, co
         if (hi > n_docs) hi = n_docs;
     }
     if (exact) {
-        rescore_kernel<<<n_queries, kRescoreWarps * 32, (size_t)dim * sizeof(float), stream>>>(q_f32, d_f32, dim, G.st);
+        {
+            ProfScope prof("dense_rescore_f32", stream);
+            rescore_kernel<<<n_queries, kRescoreWarps * 32, (size_t)dim * sizeof(float), stream>>>(q_f32, d_f32, dim, G.st);
+        }
         FZ_LAUNCH_CHECK();
         rc = cand_select<float>(G.st, n_queries, k, 0.f, true, doc_base, out_scores, out_ids, nullptr, stream);
         if (rc) return rc;

@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(kFuseThreads) fuse_kernel(const FuseParams P) 
         if (h_key[i] != kEmptyKey && h_order[i] != 0xffffffffu) {
             int pos = atomicAdd(&s_fill, 1);
             Entry e;
-            e.skey = ord64(h_acc[i]);
+            e.skey = ord64(h_acc[i] + 0.0);      // -0.0 ties with +0.0 like Python's sorted()
             e.tie = ~h_order[i];
             e.payload = (uint32_t)h_key[i];
             sort_buf[pos] = e;
@@ -468,6 +468,7 @@ int fz_fuse(const int32_t* const* ids_h, const void* const* scores_h, const int3
         FZ_CUDA(cudaFuncSetAttribute(fuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFuseSmemLimit));
         attr = true;
     }
+    ProfScope prof("fuse", (cudaStream_t)stream);
     fuse_kernel<<<n_queries, kFuseThreads, smem, (cudaStream_t)stream>>>(P);
     FZ_LAUNCH_CHECK();
     return FZ_OK;

@@ -276,6 +276,7 @@ extern "C" int fz_maxsim_bf16(const void* q_tok, int lq, const int32_t* cand_ids
     M.lq = lq;
     M.out = out_scores;
     const int grid = n_queries < num_sms() ? n_queries : num_sms();
+    ProfScope prof("maxsim", stream);
     maxsim_kernel<<<grid, kMsThreads, kMsSmem, stream>>>(maps, M);
     FZ_LAUNCH_CHECK();
     return FZ_OK;

@@ -8,6 +8,10 @@
 
 #include <cstdarg>
 #include <limits>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
 
 namespace fz {
 
@@ -20,6 +24,31 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 const char* last_error() { return g_err; }
+
+// ------------------------------------------------------------------------------------------- profiler
+struct ProfRec {
+    const char* name;
+    cudaEvent_t a, b;
+};
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static std::mutex g_prof_mu;
+
+void prof_begin(const char* name, cudaStream_t stream) {
+    if (!g_prof_on) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    ProfRec r;
+    r.name = name;
+    cudaEventCreate(&r.a);
+    cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, stream);
+    g_prof.push_back(r);
+}
+void prof_end(cudaStream_t stream) {
+    if (!g_prof_on) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (!g_prof.empty()) cudaEventRecord(g_prof.back().b, stream);
+}
 
 constexpr int kSortThreads = 1024;
 constexpr int kSmemEntries = 8192;   // 128 KB
@@ -202,6 +231,7 @@ int cand_select(const CandState<ST>& st, int n_queries, int k, ST margin, bool f
                                      kSmemEntries * (int)sizeof(Entry)));
         done = true;
     }
+    ProfScope prof(std::is_same<ST, float>::value ? "cand_select_f32" : "cand_select_f64", stream);
     cand_select_kernel<ST><<<n_queries, kSortThreads, smem, stream>>>(st, k, margin, final_out ? 1 : 0,
                                                                       (long long)doc_base, out_scores, out_ids, out_n);
     FZ_LAUNCH_CHECK();
@@ -280,6 +310,7 @@ static int launch_segsort(const ST* scores, const int32_t* ids, int n_src, long 
                                      kSmemEntries * (int)sizeof(Entry)));
         done = true;
     }
+    ProfScope prof("segsort", stream);
     segsort_kernel<ST><<<n_queries, kSortThreads, smem, stream>>>(scores, ids, n_src, src_stride, run_len, seg_stride,
                                                                   k_out, id_base, out_scores, out_ids, (Entry*)ws,
                                                                   n_pow2);
@@ -295,6 +326,40 @@ extern "C" {
 
 const char* fz_last_error(void) { return fz::last_error(); }
 int fz_abi_version(void) { return FZ_ABI_VERSION; }
+
+int fz_profile_enable(int on) {
+    std::lock_guard<std::mutex> lk(fz::g_prof_mu);
+    fz::g_prof_on = on != 0;
+    return FZ_OK;
+}
+
+int fz_profile_summary(char* out, size_t cap) {
+    std::lock_guard<std::mutex> lk(fz::g_prof_mu);
+    std::map<std::string, std::pair<int, double>> agg;
+    for (auto& r : fz::g_prof) {
+        float ms = 0.f;
+        cudaEventSynchronize(r.b);
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        auto& e = agg[r.name];
+        e.first += 1;
+        e.second += ms;
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    fz::g_prof.clear();
+    std::string s;
+    for (auto& kv : agg) {
+        char line[256];
+        snprintf(line, sizeof(line), "%s %d %.6f\n", kv.first.c_str(), kv.second.first, kv.second.second);
+        s += line;
+    }
+    if (out && cap) {
+        size_t n = s.size() < cap - 1 ? s.size() : cap - 1;
+        memcpy(out, s.data(), n);
+        out[n] = 0;
+    }
+    return FZ_OK;
+}
 
 size_t fz_merge_topk_workspace_bytes(int n_src, int n_queries, int k_in) {
     long long n = (long long)n_src * k_in;

@@ -311,7 +311,10 @@ static int sparse_topk(const fz_postings_t* ix, const int32_t* q_ptr, const int3
         const int tile_hi = (int)ceil_div<long long>(hi, ix->tile_docs);
         const long long blocks = (long long)(tile_hi - A.tile_lo) * n_queries;
         FZ_REQUIRE(blocks < (1ll << 31), "grid too large");
-        sparse_tile_kernel<AccT, 0><<<(unsigned)blocks, kSparseThreads, smem, stream>>>(A);
+        {
+            ProfScope prof(sizeof(AccT) == 8 ? "sparse_tile_f64" : "sparse_tile_f32", stream);
+            sparse_tile_kernel<AccT, 0><<<(unsigned)blocks, kSparseThreads, smem, stream>>>(A);
+        }
         FZ_LAUNCH_CHECK();
         const bool last = hi >= N;
         rc = cand_select<AccT>(A.st, n_queries, k, (AccT)0, last, doc_base, out_scores, out_ids, nullptr, stream);
@@ -321,6 +324,7 @@ static int sparse_topk(const fz_postings_t* ix, const int32_t* q_ptr, const int3
         hi = growth >= 2 ? hi * growth : hi + (cap - k);
         if (hi > N) hi = N;
     }
+    ProfScope prof("sparse_zero_fill", stream);
     sparse_zero_fill_kernel<AccT><<<n_queries, kSparseThreads, smem, stream>>>(A);
     FZ_LAUNCH_CHECK();
     return FZ_OK;

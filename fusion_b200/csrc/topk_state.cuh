@@ -47,8 +47,9 @@ inline CandState<ST> cand_state_carve(void* ws, int n_queries, int cap, int32_t*
 }
 
 #ifdef __CUDACC__
-__device__ __forceinline__ uint64_t score_key(float s) { return (uint64_t)ord32(s); }
-__device__ __forceinline__ uint64_t score_key(double s) { return ord64(s); }
+// -0.0 is folded into +0.0 first: Python's sorted() / torch treat them as equal, so they must tie (by doc id)
+__device__ __forceinline__ uint64_t score_key(float s) { return (uint64_t)ord32(s + 0.0f); }
+__device__ __forceinline__ uint64_t score_key(double s) { return ord64(s + 0.0); }
 __device__ __forceinline__ void key_score(uint64_t k, float& s) { s = unord32((uint32_t)k); }
 __device__ __forceinline__ void key_score(uint64_t k, double& s) { s = unord64(k); }
 

@@ -64,7 +64,7 @@ class LexicalIndex:
     def __init__(self, doc_ptr, doc_tok, vocab_size: int, variant: str = "bm25", k1: float = 0.9, b: float = 0.4,
                  device="cuda", doc_base: int = 0, tile_docs: int = DEFAULT_TILE_DOCS, long_min: int = LONG_LIST_MIN,
                  global_n_docs: int | None = None, global_df: np.ndarray | None = None,
-                 global_sum_dl: int | None = None):
+                 global_sum_dl: int | None = None, stats_reduce=None):
         if variant not in VARIANTS:
             raise FusionB200Error(f"unknown lexical variant {variant!r}")
         self.variant, self.k1, self.b = variant, k1, b
@@ -85,6 +85,8 @@ class LexicalIndex:
         self.term_ptr[1:] = torch.cumsum(df_local, 0)
         del ukey, tf, post_term, doc_of_tok
         # corpus-global statistics (bm25.py:133-147): N, df, avgdl = statistics.mean(doc_len)
+        if stats_reduce is not None:     # sharded build: (n_local, df_local, sum_dl_local) -> corpus-global values
+            global_n_docs, global_df, global_sum_dl = stats_reduce(self.n_docs, df_local.cpu().numpy(), int(lens.sum()))
         self.global_n_docs = int(global_n_docs if global_n_docs is not None else self.n_docs)
         df = df_local.cpu().numpy() if global_df is None else np.asarray(global_df)
         sum_dl = int(lens.sum()) if global_sum_dl is None else int(global_sum_dl)

@@ -316,11 +316,18 @@ def dense_topk(q_bf16, d_bf16, q_f32, d_f32, k: int, margin: float = 0.0, doc_ba
                                 _ptr(out_s), _ptr(out_i), _ptr(status), _ptr(ws), ws.numel(), _stream(out_s)),
               "fz_dense_topk")
 
+    # With a margin every round emits everything within `margin` of the running k-th score, about twice the k
+    # survivors of the plain filter, so the doc ranges may only grow 3x per round instead of 4x.
+    if margin > 0:
+        growth = min(growth, 3)
     run(growth)
     if bool(((status & FZ_STATUS_OVERFLOW) != 0).any()):
         if margin > 0:
-            raise FusionB200Error("dense top-k candidate buffer overflowed: lower `margin` or raise `cap`")
-        run(1)      # conservative rounds never overflow when margin == 0
+            run(2)
+            if bool(((status & FZ_STATUS_OVERFLOW) != 0).any()):
+                raise FusionB200Error("dense top-k candidate buffer overflowed: lower `margin` or raise `cap`")
+        else:
+            run(1)      # conservative rounds never overflow when margin == 0
     return out_s, out_i
 
 

@@ -33,6 +33,11 @@ typedef void* fz_stream_t; /* cudaStream_t */
 const char* fz_last_error(void);
 int fz_abi_version(void);
 
+/* Optional per-kernel timing for the benchmark: CUDA events on the launching stream around every kernel launch.
+ * fz_profile_summary synchronises, writes one "name launches total_ms" line per kernel into out, and resets. */
+int fz_profile_enable(int on);
+int fz_profile_summary(char* out, size_t cap);
+
 /* per-query status bits written by the top-k entry points */
 #define FZ_STATUS_OVERFLOW 1  /* candidate buffer overflowed: result for this query is NOT valid, re-run with growth=1 */
 #define FZ_STATUS_NEED_ZERO 2 /* fewer than k positive-score docs: zero-score docs were appended in doc-id order */

@@ -1,0 +1,42 @@
+"""The C-ABI shared library loads without a GPU and exports every symbol include/fusion_b200.h declares."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    with open(os.path.join(ROOT, "include", "fusion_b200.h")) as fh:
+        text = re.sub(r"/\*.*?\*/", "", fh.read(), flags=re.S)
+    return sorted(set(re.findall(r"\b(fz_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported_and_bound():
+    from fusion_b200 import _lib
+    lib = _lib.load()
+    names = _declared()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in the header but not exported"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
+    assert sorted(_lib.SIGNATURES) == names
+    assert lib.fz_abi_version() == 1
+
+
+def test_argument_errors_are_reported_without_a_gpu():
+    from fusion_b200 import _lib
+    lib = _lib.load()
+    rc = lib.fz_merge_topk_f32(None, None, 1, 1, 1, 1, None, None, None, 0, None)
+    assert rc == -1 and b"null" in lib.fz_last_error()
+    rc = lib.fz_dense_topk(None, None, None, None, 1, 10, 100, 1, ctypes.c_float(0), 0, 64, 4, None, None, None, None, 0, None)
+    assert rc == -1
+    with pytest.raises(_lib.FusionB200Error):
+        _lib.check(rc, "fz_dense_topk")
+
+
+def test_postings_struct_matches_header_layout():
+    from fusion_b200 import _lib
+    assert ctypes.sizeof(_lib.Postings) == 5 * 8 + 4 + 4 + 8 + 4 + 4

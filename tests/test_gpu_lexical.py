@@ -1,0 +1,133 @@
+"""GPU parity: K2 (BM25 / TF-IDF / ATIRE and SPLADE inverted-index scoring) against the reference goldens and the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from fusion_b200 import synth
+from oracle import bm25 as obm25
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("tag,cls_name,kw", [("tfidf", "TFIDF", {}), ("bm25", "BM25", dict(k1=2.5, b=0.2)),
+                                             ("bm25_mm", "BM25", dict(k1=0.9, b=0.4)), ("atire", "AtireBM25", dict(k1=0.9, b=0.4))])
+def test_lexical_golden_full_ranking(golden_dir, tag, cls_name, kw):
+    """Every document ranked for every query, bit-exact ids and fp64 scores vs the verbatim reference classes:
+    negative idf, OOV tokens, repeated tokens, duplicate documents (ties by lower index), all-zero queries."""
+    from fusion_b200.retrievers import bm25 as mod
+    g = np.load(os.path.join(golden_dir, "lexical_small.npz"))
+    docs, queries = [str(x) for x in g["docs"]], [str(x) for x in g["queries"]]
+    r = getattr(mod, cls_name)(docs, **kw)
+    res = r.search_all(queries, top_k=len(docs))
+    for qi in range(len(queries)):
+        assert [x["corpus_id"] for x in res[qi]] == g[f"{tag}_ids"][qi].tolist(), (tag, qi)
+        assert np.array_equal(np.array([x["score"] for x in res[qi]]), g[f"{tag}_scores"][qi]), (tag, qi)
+    # the materialise-and-sort path (fz_sparse_scores_f64 + fz_rank_rows_f64) used when top_k is large
+    from fusion_b200 import ops
+    q_ptr, q_term = r._encode_queries(queries)
+    sc, ids = ops.rank_rows(ops.sparse_scores(r.index.view(), q_ptr, q_term), len(docs))
+    assert np.array_equal(ids.cpu().numpy(), g[f"{tag}_ids"])
+    assert np.array_equal(sc.cpu().numpy(), g[f"{tag}_scores"])
+
+
+@pytest.mark.parametrize("k", [1, 10, 100])
+@pytest.mark.parametrize("tag,cls_name,kw", [("bm25", "BM25", dict(k1=2.5, b=0.2)), ("tfidf", "TFIDF", {})])
+def test_lexical_golden_topk_pipeline(golden_dir, tag, cls_name, kw, k):
+    """Same fixture through the threshold-filter top-k pipeline (tiny tiles force several rounds and tiles),
+    including the zero-fill (fewer than k matches) and negative-tail paths."""
+    from fusion_b200.retrievers import bm25 as mod
+    g = np.load(os.path.join(golden_dir, "lexical_small.npz"))
+    docs, queries = [str(x) for x in g["docs"]], [str(x) for x in g["queries"]]
+    r = getattr(mod, cls_name)(docs, tile_docs=256, long_min=8, **kw)
+    sc, ids = r.search_all_tensors(queries, top_k=k)
+    assert np.array_equal(ids.cpu().numpy(), g[f"{tag}_ids"][:, :k])
+    assert np.array_equal(sc.cpu().numpy(), g[f"{tag}_scores"][:, :k])
+
+
+def test_lexical_c1_slice_golden(golden_dir):
+    from fusion_b200.retrievers.bm25 import BM25
+    g = np.load(os.path.join(golden_dir, "lexical_c1_slice.npz"))
+    (dptr, dtok), (qptr, qtok) = synth.c1_lexical(n_docs=int(g["n_docs"]), n_queries=int(g["n_queries"]))
+    docs, queries = synth.ids_to_strings(dptr, dtok), synth.ids_to_strings(qptr, qtok)
+    r = BM25(docs, k1=2.5, b=0.2, tile_docs=1024, long_min=64)
+    sc, ids = r.search_all_tensors(queries, top_k=int(g["top_k"]))
+    assert np.array_equal(ids.cpu().numpy(), g["ids"])
+    assert np.array_equal(sc.cpu().numpy(), g["scores"])
+
+
+def test_bm25_zero_division_like_reference():
+    from fusion_b200.retrievers.bm25 import BM25
+    r = BM25(["a b", "b c"], k1=0.0, b=0.5)
+    with pytest.raises(ZeroDivisionError):
+        r.search("a", top_k=2)
+
+
+def _token_queries(qptr, qtok, vocab, dev):
+    t = np.where(qtok < vocab, qtok, -1).astype(np.int32)
+    return torch.from_numpy(qptr.astype(np.int32)).to(dev), torch.from_numpy(t).to(dev)
+
+
+@pytest.mark.parametrize("n_docs,vocab,k,tile,cap", [(60000, 20000, 100, 8192, 8192), (30000, 500, 1000, 2048, 2048)])
+def test_bm25_c3_shaped_vs_oracle(n_docs, vocab, k, tile, cap):
+    """mMARCO-shaped token statistics (k1=0.9, b=0.4) at a size the oracle finishes in seconds: bit-exact."""
+    from fusion_b200 import ops
+    from fusion_b200.index import LexicalIndex
+    (dptr, dtok), (qptr, qtok) = synth.c3_lexical(n_docs, 48, vocab)
+    ix = LexicalIndex(dptr, dtok, vocab, "bm25", 0.9, 0.4, tile_docs=tile, long_min=256)
+    q_ptr, q_term = _token_queries(qptr, qtok, vocab, ix.device)
+    sc, ids = ops.sparse_topk(ix.view(), q_ptr, q_term, None, k, cap=cap)
+    o = obm25.LexicalOracle(dptr, dtok, vocab, "bm25", 0.9, 0.4)
+    for qi in range(48):
+        t = qtok[qptr[qi]:qptr[qi + 1]]
+        eids, esc = o.search_ids(np.where(t < vocab, t, -1), k)
+        assert np.array_equal(ids[qi].cpu().numpy(), eids), qi
+        assert np.array_equal(sc[qi].cpu().numpy(), esc), qi
+
+
+def test_bm25_sharded_equals_unsharded():
+    """Two doc-range shards with corpus-global statistics, merged with the k-way merge == one index."""
+    from fusion_b200 import ops
+    from fusion_b200.index import LexicalIndex
+    n_docs, vocab, k = 20000, 3000, 200
+    (dptr, dtok), (qptr, qtok) = synth.c3_lexical(n_docs, 16, vocab)
+    full = LexicalIndex(dptr, dtok, vocab, "bm25", 0.9, 0.4, tile_docs=2048)
+    q_ptr, q_term = _token_queries(qptr, qtok, vocab, full.device)
+    sc, ids = ops.sparse_topk(full.view(), q_ptr, q_term, None, k)
+    cut = 9000
+    parts = []
+    for lo, hi in ((0, cut), (cut, n_docs)):
+        p = dptr[lo:hi + 1] - dptr[lo]
+        t = dtok[dptr[lo]:dptr[hi]]
+        ix = LexicalIndex(p, t, vocab, "bm25", 0.9, 0.4, doc_base=lo, tile_docs=2048, global_n_docs=n_docs,
+                          global_df=full.df, global_sum_dl=int(dptr[-1]))
+        parts.append(ops.sparse_topk(ix.view(), q_ptr, q_term, None, k, doc_base=lo))
+    ms, mi = ops.merge_topk(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]), k)
+    assert torch.equal(mi, ids) and torch.equal(ms, sc)
+
+
+@pytest.mark.parametrize("sim", ["cos_sim", "dot"])
+def test_splade_sparse_vs_dense_oracle(sim):
+    """SPLADE: the reference scores dense [.,V] vectors with cosine (hybrid.py:101-103); the inverted index must
+    agree to 1e-5 on scores and on the top-k set (ties at the cut excluded)."""
+    from fusion_b200 import ops
+    from fusion_b200.index import SparseIndex, sparse_queries
+    from oracle import dense as odense
+    vocab, n_docs, nq, k = 2000, 6000, 12, 100
+    dp, dt, dw = synth.splade_vectors(n_docs, vocab, 60, 8, 200, seed=311)
+    qp, qt, qw = synth.splade_vectors(nq, vocab, 12, 2, 40, seed=312)
+    ix = SparseIndex(dp, dt, dw, vocab, sim, tile_docs=1024, long_min=64)
+    q_ptr, q_term, q_w = sparse_queries(qp, qt, qw, sim, ix.device)
+    sc, ids = ops.sparse_topk(ix.view(), q_ptr, q_term, q_w, k)
+    full = ops.sparse_scores(ix.view(), q_ptr, q_term, q_w).cpu()
+    dd, qd = torch.from_numpy(synth.densify(dp, dt, dw, vocab)), torch.from_numpy(synth.densify(qp, qt, qw, vocab))
+    ref = odense.similarity(qd, dd, sim)
+    torch.testing.assert_close(full, ref, rtol=1e-5, atol=1e-5)
+    esc, eids = odense.topk_tensors(qd, dd, k, sim)
+    torch.testing.assert_close(sc.cpu(), esc, rtol=1e-5, atol=1e-5)
+    for qi in range(nq):
+        cut = float(esc[qi, -1])
+        a = {int(i) for i, s in zip(ids[qi].cpu(), sc[qi].cpu()) if s > cut + 1e-5}
+        b = {int(i) for i, s in zip(eids[qi], esc[qi]) if s > cut + 1e-5}
+        assert a == b

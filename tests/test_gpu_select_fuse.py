@@ -1,0 +1,132 @@
+"""GPU parity: K5 merge / rank rows and K4 fusion against the oracle and the reference goldens (through the C ABI)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import fusion as ofusion
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from fusion_b200 import ops
+    return ops
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("g,q,k_in,k_out", [(2, 5, 50, 50), (8, 33, 1000, 1000), (4, 3, 3000, 100)])
+def test_merge_topk(dtype, g, q, k_in, k_out):
+    ops = _ops()
+    gen = torch.Generator().manual_seed(g * 1000 + k_in)
+    sc = torch.randn(g, q, k_in, generator=gen, dtype=torch.float64).to(dtype)
+    sc = (sc * 8).round() / 8                      # many exact ties
+    ids = torch.stack([torch.randperm(g * k_in * 2, generator=gen)[: g * k_in].reshape(g, k_in) for _ in range(q)], 1).to(torch.int32)
+    ids[0, 0, :3] = -1                             # padding entries are ignored
+    out_s, out_i = ops.merge_topk(sc.cuda(), ids.cuda(), k_out)
+    for qi in range(q):
+        s, i = sc[:, qi].reshape(-1), ids[:, qi].reshape(-1).long()
+        keep = i >= 0
+        s, i = s[keep], i[keep]
+        order = np.lexsort((i.numpy(), -s.double().numpy()))[:k_out]
+        assert out_i[qi].cpu().tolist() == i[order].tolist()
+        assert torch.equal(out_s[qi].cpu(), s[order])
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("n,k", [(700, 700), (5000, 123), (20000, 20000), (40000, 1000)])
+def test_rank_rows(dtype, n, k):
+    ops = _ops()
+    gen = torch.Generator().manual_seed(n)
+    sc = ((torch.randn(3, n, generator=gen, dtype=torch.float64) * 16).round() / 16).to(dtype)
+    sc[1, : n // 2] = 0.0
+    out_s, out_i = ops.rank_rows(sc.cuda(), k, doc_base=7)
+    for qi in range(3):
+        order = np.argsort(-sc[qi].double().numpy(), kind="stable")[:k]
+        assert np.array_equal(out_i[qi].cpu().numpy(), order + 7)
+        assert torch.equal(out_s[qi].cpu(), sc[qi][order])
+
+
+FUSION_CASES = [("bcf", None), ("rrf", None)] + [("nsf", n) for n in ofusion.NORMALIZATIONS]
+
+
+@pytest.mark.parametrize("method,norm", FUSION_CASES)
+def test_fuse_golden(golden_dir, method, norm):
+    """Fixtures produced by the verbatim reference Aggregator.fuse (oracle/make_golden.py)."""
+    ops = _ops()
+    g = np.load(os.path.join(golden_dir, "fusion_small.npz"))
+    systems = [str(s) for s in g["systems"]]
+    tag = method if norm is None else f"{method}_{norm}"
+    exp_ids, exp_sc = g[f"out_ids_{tag}"], g[f"out_scores_{tag}"]
+    lists = [(torch.from_numpy(g[f"in_ids_{s}"]).cuda(), torch.from_numpy(g[f"in_scores_{s}"]).cuda(), None) for s in systems]
+    ids, sc, lens = ops.fuse(lists, method, norm, list(g["weights"]), [g[f"distr_{s}"] for s in systems])
+    ids, sc, lens = ids.cpu().numpy(), sc.cpu().numpy(), lens.cpu().numpy()
+    for qi in range(exp_ids.shape[0]):
+        n = int((exp_ids[qi] >= 0).sum())
+        assert lens[qi] == n
+        tol = 1e-12 if (method != "nsf" or norm == "none") else 1e-5
+        np.testing.assert_allclose(sc[qi, :n], exp_sc[qi, :n], rtol=tol, atol=tol)
+        got, exp = ids[qi, :n].tolist(), exp_ids[qi, :n].tolist()
+        if got != exp:      # only near-ties (fp32 normalisation rounding) may swap
+            for a, b in zip(got, exp):
+                if a != b:
+                    sa, sb = exp_sc[qi, exp.index(a)], exp_sc[qi, exp.index(b)]
+                    assert abs(sa - sb) <= 1e-5 * max(1.0, abs(sa)), (tag, qi, a, b)
+
+
+def _random_lists(rng, q, n_list, pool):
+    lists = []
+    for n in n_list:
+        ids = np.stack([rng.choice(pool, n, replace=False) for _ in range(q)]).astype(np.int32)
+        sc = -np.sort(-rng.normal(0, 2, (q, n)), axis=1)
+        lists.append((ids, sc))
+    return lists
+
+
+@pytest.mark.parametrize("n_list,pool", [([1000, 1000, 1000, 1000], 3000), ([3000, 2500], 4000), ([28000, 28000], 28000)])
+@pytest.mark.parametrize("method,norm", [("rrf", None), ("bcf", None), ("nsf", "z-score"), ("nsf", "min-max"), ("nsf", "none")])
+def test_fuse_vs_oracle(method, norm, n_list, pool):
+    """Shared-memory path (4 x 1000), global-workspace path and the reference's full-length lists (n = N = 28k)."""
+    ops = _ops()
+    rng = np.random.Generator(np.random.PCG64(len(n_list) * 7 + pool))
+    q = 3
+    host = _random_lists(rng, q, n_list, pool)
+    w = [1.0 / len(n_list)] * len(n_list)
+    lists = [(torch.from_numpy(i).cuda(), torch.from_numpy(s).cuda(), None) for i, s in host]
+    ids, sc, lens = ops.fuse(lists, method, norm, w)
+    ids, sc, lens = ids.cpu().numpy(), sc.cpu().numpy(), lens.cpu().numpy()
+    for qi in range(q):
+        eids, esc = ofusion.fuse_query([h[0][qi] for h in host], [h[1][qi] for h in host], method, norm, w)
+        esc = np.asarray(esc, dtype=np.float64)
+        n = len(eids)
+        assert lens[qi] == n
+        tol = 1e-12 if (method != "nsf" or norm == "none") else 1e-5
+        np.testing.assert_allclose(sc[qi, :n], esc, rtol=tol, atol=tol)
+        if method != "nsf" or norm == "none":
+            assert ids[qi, :n].tolist() == eids                     # exact sequence incl. insertion-order ties
+        else:
+            assert sorted(ids[qi, :n].tolist()) == sorted(eids)
+            mism = np.flatnonzero(ids[qi, :n] != np.asarray(eids))
+            for p in mism:                                          # swaps only between near-equal fused scores
+                assert abs(esc[p] - esc[eids.index(int(ids[qi, p]))]) <= 2e-5
+
+
+def test_fuse_ragged_and_float32_inputs():
+    ops = _ops()
+    rng = np.random.Generator(np.random.PCG64(5))
+    q = 4
+    host = _random_lists(rng, q, [40, 30], 60)
+    lens0 = np.array([40, 0, 17, 2], dtype=np.int32)   # (a 1-element list gives z-score NaN in the reference)
+    lists = [(torch.from_numpy(host[0][0]).cuda(), torch.from_numpy(host[0][1]).cuda(), torch.from_numpy(lens0).cuda()),
+             (torch.from_numpy(host[1][0]).cuda(), torch.from_numpy(host[1][1].astype(np.float32)).cuda(), None)]
+    ids, sc, lens = ops.fuse(lists, "nsf", "z-score", [0.3, 0.7])
+    for qi in range(q):
+        eids, esc = ofusion.fuse_query([host[0][0][qi, :lens0[qi]], host[1][0][qi]],
+                                       [host[0][1][qi, :lens0[qi]], host[1][1][qi].astype(np.float32).astype(np.float64)],
+                                       "nsf", "z-score", [0.3, 0.7])
+        n = len(eids)
+        assert int(lens[qi]) == n
+        got = np.asarray(sc[qi, :n].cpu())
+        exp = np.asarray(esc, dtype=np.float64)
+        np.testing.assert_allclose(got, exp, rtol=1e-5, atol=1e-5, equal_nan=True)
