@@ -1,0 +1,86 @@
+// CTA-wide radix select: the k-th largest of n composite keys (hi : lo) held in shared memory, most significant
+// byte first.  Keys are unique when `lo` carries a unique tie-breaker (~doc id), so "key >= k-th key" selects
+// exactly k records.  Every pass histograms one byte of the keys that still match the decided prefix (8-12 cheap
+// passes over <= 8192 records) instead of sorting all records.
+#pragma once
+
+#include <cstdint>
+
+namespace fz {
+
+template <typename HiT>
+struct KeyBits;
+template <>
+struct KeyBits<uint32_t> { static constexpr int hi_bits = 32; };
+template <>
+struct KeyBits<uint64_t> { static constexpr int hi_bits = 64; };
+
+// hist: 256 counters in shared memory; bcast: 2 ints in shared memory.  All threads of the CTA must call.
+// Requires 1 <= k <= n.  On return (kth_hi, kth_lo) is the k-th largest key.
+template <typename HiT>
+__device__ void cta_radix_select_kth(const HiT* __restrict__ hi, const uint32_t* __restrict__ lo, int n, int k,
+                                     int* hist, int* bcast, HiT& kth_hi, uint32_t& kth_lo) {
+    constexpr int HB = KeyBits<HiT>::hi_bits;
+    HiT p_hi = 0, m_hi = 0;          // decided prefix bits / their mask, hi word
+    uint32_t p_lo = 0, m_lo = 0;     // same, lo word
+    int remaining = k;
+    for (int shift = HB + 32 - 8; shift >= 0; shift -= 8) {
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+        __syncthreads();
+        const bool in_hi = shift >= 32;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const HiT h = hi[i];
+            const uint32_t l = lo[i];
+            if ((h & m_hi) == p_hi && (l & m_lo) == p_lo) {
+                const uint32_t d = in_hi ? (uint32_t)(h >> (shift - 32)) & 255u : (l >> shift) & 255u;
+                atomicAdd(&hist[d], 1);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            // lane l owns bins 255-8l .. 248-8l (descending); find the bin where the running count reaches `remaining`
+            const int lane = threadIdx.x;
+            int c[8], s = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { c[j] = hist[255 - 8 * lane - j]; s += c[j]; }
+            int incl = s;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const int excl = incl - s;
+            if (excl < remaining && remaining <= incl) {
+                int run = excl;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (run < remaining && remaining <= run + c[j]) {
+                        bcast[0] = 255 - 8 * lane - j;      // the digit of the k-th key
+                        bcast[1] = remaining - run;         // rank inside that bin
+                    }
+                    run += c[j];
+                }
+            }
+        }
+        __syncthreads();
+        const uint32_t d = (uint32_t)bcast[0];
+        remaining = bcast[1];
+        if (in_hi) {
+            p_hi |= (HiT)d << (shift - 32);
+            m_hi |= (HiT)255 << (shift - 32);
+        } else {
+            p_lo |= d << shift;
+            m_lo |= 255u << shift;
+        }
+        __syncthreads();
+    }
+    kth_hi = p_hi;
+    kth_lo = p_lo;
+}
+
+template <typename HiT>
+__device__ __forceinline__ bool key_ge(HiT a_hi, uint32_t a_lo, HiT b_hi, uint32_t b_lo) {
+    return a_hi > b_hi || (a_hi == b_hi && a_lo >= b_lo);
+}
+
+}  // namespace fz

@@ -5,6 +5,7 @@
 // a global workspace with the short-stride stages done on 4096-record chunks staged through shared memory.
 #include "common.cuh"
 #include "topk_state.cuh"
+#include "radix_select.cuh"
 
 #include <cstdarg>
 #include <limits>
@@ -112,6 +113,8 @@ __device__ void bitonic_sort_large(Entry* a, int n_pow2, Entry* sm) {
     }
 }
 
+__device__ __forceinline__ size_t align_up_dev(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
 __device__ __forceinline__ Entry pad_entry() {
     Entry e;
     e.skey = 0;
@@ -133,76 +136,96 @@ __global__ void cand_init_kernel(CandState<ST> st, int n_queries) {
     }
 }
 
+// One CTA per query.  The buffer's records are staged in shared memory as composite keys (order-preserving
+// score bits : ~doc id); a radix select finds the k-th largest key, everything that survives the new threshold is
+// written back compacted (unsorted - only the final round sorts, and then just the k winners).
+template <typename ST> struct HiOf;
+template <> struct HiOf<float> { using type = uint32_t; };
+template <> struct HiOf<double> { using type = uint64_t; };
+__device__ __forceinline__ void hi_score(uint32_t h, float& s) { s = unord32(h); }
+__device__ __forceinline__ void hi_score(uint64_t h, double& s) { s = unord64(h); }
+
 template <typename ST>
 __global__ void __launch_bounds__(kSortThreads) cand_select_kernel(CandState<ST> st, int k, ST margin, int final_out,
                                                                    long long doc_base, ST* out_scores,
-                                                                   int32_t* out_ids, int32_t* out_n) {
+                                                                   int32_t* out_ids, int32_t* out_n, int k_pow2) {
+    using HiT = typename HiOf<ST>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    Entry* sm = reinterpret_cast<Entry*>(smem_raw);
-    __shared__ int s_keep;
+    HiT* s_hi = reinterpret_cast<HiT*>(smem_raw);                               // [cap]
+    uint32_t* s_lo = reinterpret_cast<uint32_t*>(s_hi + st.cap);                // [cap]
+    Entry* s_sort = reinterpret_cast<Entry*>(smem_raw + align_up_dev((size_t)st.cap * (sizeof(HiT) + 4), 16));   // [k_pow2]
+    __shared__ int s_hist[256];
+    __shared__ int s_bcast[2];
+    __shared__ int s_keep, s_win;
+
     const int q = blockIdx.x;
     const int raw = st.cnt[q];
     const int n = min(raw, st.cap);
     if (threadIdx.x == 0) {
         s_keep = 0;
+        s_win = 0;
         if (raw > st.cap) st.status[q] |= FZ_STATUS_OVERFLOW;
     }
-    int n_pow2 = 1;
-    while (n_pow2 < n) n_pow2 <<= 1;
     const size_t off = (size_t)q * st.cap;
-    for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
-        Entry e = pad_entry();
-        if (i < n) {
-            int32_t d = st.id[off + i];
-            e.skey = score_key(st.score[off + i]);
-            e.tie = ~(uint32_t)d;
-            e.payload = (uint32_t)d;
-        }
-        sm[i] = e;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        s_hi[i] = (HiT)score_key(st.score[off + i]);
+        s_lo[i] = ~(uint32_t)st.id[off + i];
     }
     __syncthreads();
-    bitonic_sort_cta(sm, n_pow2);
 
-    int keep = n;
     ST tau = st.tau[q];
-    if (n >= k) {
+    HiT kth_hi = 0;
+    uint32_t kth_lo = 0;
+    const bool full = n >= k;
+    if (full) {
+        cta_radix_select_kth<HiT>(s_hi, s_lo, n, k, s_hist, s_bcast, kth_hi, kth_lo);
         ST kth;
-        key_score(sm[k - 1].skey, kth);
-        ST t = kth - margin;
+        hi_score(kth_hi, kth);
+        const ST t = kth - margin;
         if (t > tau) tau = t;
-        if (margin == (ST)0) {
-            // Rounds visit docs in ascending id order, so a later doc that merely ties the k-th score loses the
-            // tie (lower id first): keep exactly k and let the scoring kernels emit on score > tau.
-            keep = k;
-        } else {
-            // records are sorted: count those still >= tau
-            const uint64_t tk = score_key(tau);
-            int local = 0;
-            for (int i = threadIdx.x; i < n; i += blockDim.x) local += (sm[i].skey >= tk) ? 1 : 0;
-            local = warp_sum(local);
-            if ((threadIdx.x & 31) == 0 && local) atomicAdd(&s_keep, local);
-            __syncthreads();
-            keep = s_keep;
+    }
+    // survivors: exactly the k best when margin == 0 (a later doc that only ties the k-th score loses the tie:
+    // rounds visit docs in ascending id order), everything with score >= tau otherwise; all records if n < k
+    const HiT tau_hi = (HiT)score_key(tau);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const HiT h = s_hi[i];
+        const uint32_t l = s_lo[i];
+        const bool win = !full || key_ge<HiT>(h, l, kth_hi, kth_lo);
+        const bool keep = !full || (margin == (ST)0 ? win : h >= tau_hi);
+        if (keep) {
+            const int p = atomicAdd(&s_keep, 1);
+            ST s;
+            hi_score(h, s);
+            st.score[off + p] = s;
+            st.id[off + p] = (int32_t)~l;
+        }
+        if (final_out && win) {
+            const int p = atomicAdd(&s_win, 1);
+            Entry e;
+            e.skey = (uint64_t)h;
+            e.tie = l;
+            e.payload = ~l;
+            s_sort[p] = e;
         }
     }
-    for (int i = threadIdx.x; i < keep; i += blockDim.x) {
-        ST s;
-        key_score(sm[i].skey, s);
-        st.score[off + i] = s;
-        st.id[off + i] = (int32_t)sm[i].payload;
-    }
+    __syncthreads();
     if (threadIdx.x == 0) {
-        st.cnt[q] = keep;
+        st.cnt[q] = s_keep;
         st.tau[q] = tau;
     }
     if (final_out) {
-        const int m = min(keep, k);
+        const int m = s_win;        // min(n, k)
+        int m2 = 1;
+        while (m2 < m) m2 <<= 1;
+        for (int i = m + threadIdx.x; i < m2; i += blockDim.x) s_sort[i] = pad_entry();
+        __syncthreads();
+        bitonic_sort_cta(s_sort, m2);
         for (int i = threadIdx.x; i < k; i += blockDim.x) {
             ST s = -std::numeric_limits<ST>::infinity();
             int32_t d = -1;
             if (i < m) {
-                key_score(sm[i].skey, s);
-                d = (int32_t)(doc_base + (long long)sm[i].payload);
+                hi_score((HiT)s_sort[i].skey, s);
+                d = (int32_t)(doc_base + (long long)s_sort[i].payload);
             }
             out_scores[(size_t)q * k + i] = s;
             out_ids[(size_t)q * k + i] = d;
@@ -223,17 +246,20 @@ int cand_select(const CandState<ST>& st, int n_queries, int k, ST margin, bool f
                 ST* out_scores, int32_t* out_ids, int32_t* out_n, cudaStream_t stream) {
     FZ_REQUIRE(st.cap <= kSmemEntries, "candidate capacity %d exceeds %d", st.cap, kSmemEntries);
     FZ_REQUIRE(k >= 1 && k <= st.cap, "k=%d must be in [1, cap=%d]", k, st.cap);
-    size_t smem = (size_t)next_pow2(st.cap) * sizeof(Entry);
+    using HiT = typename HiOf<ST>::type;
+    const int k_pow2 = next_pow2(k);
+    size_t smem = align_up((size_t)st.cap * (sizeof(HiT) + 4), 16) + (size_t)k_pow2 * sizeof(Entry);
+    FZ_REQUIRE(smem <= 200 * 1024, "cap=%d / k=%d need %zu bytes of shared memory", st.cap, k, smem);
     static bool attr_f = false, attr_d = false;
     bool& done = std::is_same<ST, float>::value ? attr_f : attr_d;
     if (!done) {
-        FZ_CUDA(cudaFuncSetAttribute(cand_select_kernel<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     kSmemEntries * (int)sizeof(Entry)));
+        FZ_CUDA(cudaFuncSetAttribute(cand_select_kernel<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         done = true;
     }
     ProfScope prof(std::is_same<ST, float>::value ? "cand_select_f32" : "cand_select_f64", stream);
     cand_select_kernel<ST><<<n_queries, kSortThreads, smem, stream>>>(st, k, margin, final_out ? 1 : 0,
-                                                                      (long long)doc_base, out_scores, out_ids, out_n);
+                                                                      (long long)doc_base, out_scores, out_ids, out_n,
+                                                                      k_pow2);
     FZ_LAUNCH_CHECK();
     return FZ_OK;
 }

@@ -16,8 +16,8 @@
 
 namespace fz {
 
-constexpr int kSparseThreads = 512;
-constexpr int kMaxTermsPerPass = 128;
+constexpr int kSparseThreads = 128;      // small CTAs: the per-term barrier only couples 4 warps, 16 CTAs per SM hide latency
+constexpr int kMaxTermsPerPass = 64;
 
 // ------------------------------------------------------------------------------------ index-time helpers
 __global__ void lexical_impacts_kernel(const int64_t* __restrict__ term_ptr, const int32_t* __restrict__ post_doc,
@@ -92,6 +92,9 @@ template <> struct ValOf<double> { using type = double; };
 template <> struct ValOf<float> { using type = float; };
 
 // Accumulate one query's postings that fall into docs [d_lo, d_hi) into acc[0 .. d_hi-d_lo) (shared memory).
+// Terms are applied one after the other: the barrier between terms keeps every doc's sum in query order and makes
+// atomics unnecessary (one term never hits a doc twice).  (A register-prefetch of the next term's first chunk was
+// measured slower: the kernel is bound by L2 traffic and issue slots, not by exposed latency.)
 template <typename AccT>
 __device__ __forceinline__ void accumulate_tile(const SparseArgs<AccT>& A, int q, int tile, long long d_lo,
                                                 long long d_hi, AccT* acc, long long* t_lo, long long* t_hi,
@@ -100,7 +103,12 @@ __device__ __forceinline__ void accumulate_tile(const SparseArgs<AccT>& A, int q
     const ValT* __restrict__ vals = reinterpret_cast<const ValT*>(A.ix.post_val);
     const int32_t* __restrict__ docs = A.ix.post_doc;
     const int n = (int)(d_hi - d_lo);
-    for (int i = threadIdx.x; i < n; i += blockDim.x) acc[i] = (AccT)0;
+    const int dl = (int)d_lo;
+    {   // zero the tile's accumulators with 16-byte stores (the buffer is 16-byte aligned and padded)
+        int4* z = reinterpret_cast<int4*>(acc);
+        const int n16 = (n * (int)sizeof(AccT) + 15) / 16;
+        for (int i = threadIdx.x; i < n16; i += blockDim.x) z[i] = make_int4(0, 0, 0, 0);
+    }
     const int qb = A.q_ptr[q], qe = A.q_ptr[q + 1];
     for (int pass = qb; pass < qe; pass += kMaxTermsPerPass) {
         const int nt = min(kMaxTermsPerPass, qe - pass);
@@ -127,18 +135,28 @@ __device__ __forceinline__ void accumulate_tile(const SparseArgs<AccT>& A, int q
         }
         __syncthreads();
         for (int j = 0; j < nt; ++j) {
-            const long long lo = t_lo[j], hi = t_hi[j];
-            for (long long p = lo + threadIdx.x; p < hi; p += blockDim.x) {
-                const long long d = docs[p];
-                if (d >= d_lo && d < d_hi) {
-                    if constexpr (std::is_same<AccT, double>::value) {
-                        acc[d - d_lo] = __dadd_rn(acc[d - d_lo], vals[p]);
-                    } else {
-                        acc[d - d_lo] = __fmaf_rn(vals[p], t_w[j], acc[d - d_lo]);
-                    }
+            const int32_t* __restrict__ dj = docs + t_lo[j];
+            const ValT* __restrict__ vj = vals + t_lo[j];
+            const int len = (int)(t_hi[j] - t_lo[j]);
+            const float w = t_w[j];
+            // two postings per thread and iteration, doc and value loads issued together (no load behind a branch)
+            for (int p = threadIdx.x; p < len; p += 2 * blockDim.x) {
+                const int p1 = p + blockDim.x;
+                const bool ok1 = p1 < len;
+                const int d0 = __ldg(dj + p);
+                const ValT v0 = __ldg(vj + p);
+                const int d1 = ok1 ? __ldg(dj + p1) : dl - 1;
+                const ValT v1 = ok1 ? __ldg(vj + p1) : (ValT)0;
+                const unsigned o0 = (unsigned)(d0 - dl), o1 = (unsigned)(d1 - dl);   // one unsigned compare covers both bounds
+                if constexpr (std::is_same<AccT, double>::value) {
+                    if (o0 < (unsigned)n) acc[o0] = __dadd_rn(acc[o0], v0);
+                    if (o1 < (unsigned)n) acc[o1] = __dadd_rn(acc[o1], v1);
+                } else {
+                    if (o0 < (unsigned)n) acc[o0] = __fmaf_rn(v0, w, acc[o0]);
+                    if (o1 < (unsigned)n) acc[o1] = __fmaf_rn(v1, w, acc[o1]);
                 }
             }
-            __syncthreads();   // next term may hit the same docs; keeps the per-doc sum in query order
+            __syncthreads();   // the next term may hit the same docs
         }
     }
     __syncthreads();
@@ -150,7 +168,6 @@ __global__ void __launch_bounds__(kSparseThreads) sparse_tile_kernel(const Spars
     AccT* acc = reinterpret_cast<AccT*>(smem_raw);
     __shared__ long long t_lo[kMaxTermsPerPass], t_hi[kMaxTermsPerPass];
     __shared__ float t_w[kMaxTermsPerPass];
-    __shared__ int s_pos, s_neg;
 
     const int tile = A.tile_lo + blockIdx.x / A.n_queries;
     const int q = blockIdx.x % A.n_queries;
@@ -161,7 +178,6 @@ __global__ void __launch_bounds__(kSparseThreads) sparse_tile_kernel(const Spars
         d_hi = min(d_hi, A.r_hi);
     }
     if (d_hi <= d_lo) return;
-    if (threadIdx.x == 0) { s_pos = 0; s_neg = 0; }
     accumulate_tile<AccT>(A, q, tile, d_lo, d_hi, acc, t_lo, t_hi, t_w);
     const int n = (int)(d_hi - d_lo);
     if (MODE == 1) {
@@ -170,24 +186,18 @@ __global__ void __launch_bounds__(kSparseThreads) sparse_tile_kernel(const Spars
         return;
     }
     const AccT tau = A.st.tau[q];
-    int pos = 0, neg = 0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const AccT s = acc[i];
-        pos += s > (AccT)0;
-        neg += s < (AccT)0;
-        const bool want = A.sign_mode > 0 ? (s > (AccT)0) : (s < (AccT)0);
-        if (want && s > tau) cand_append<AccT>(A.st, q, s, (int32_t)(d_lo + i));
-    }
-    pos = warp_sum(pos);
-    neg = warp_sum(neg);
-    if ((threadIdx.x & 31) == 0) {
-        if (pos) atomicAdd(&s_pos, pos);
-        if (neg) atomicAdd(&s_neg, neg);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        if (s_pos) atomicAdd(&A.st.npos[q], s_pos);
-        if (s_neg) atomicAdd(&A.st.nneg[q], s_neg);
+    // scan the tile 16 bytes at a time; survivors are rare once tau has risen, so the common case is one compare
+    constexpr int V = 16 / (int)sizeof(AccT);
+    const AccT lim = A.sign_mode > 0 ? (tau > (AccT)0 ? tau : (AccT)0) : tau;
+    for (int i0 = threadIdx.x * V; i0 < n; i0 += blockDim.x * V) {
+        AccT v[V];
+        *reinterpret_cast<int4*>(v) = *reinterpret_cast<const int4*>(acc + i0);
+#pragma unroll
+        for (int u = 0; u < V; ++u) {
+            const AccT sc = v[u];
+            const bool want = A.sign_mode > 0 ? (sc > lim) : (sc < (AccT)0 && sc > lim);
+            if (want && i0 + u < n) cand_append<AccT>(A.st, q, sc, (int32_t)(d_lo + i0 + u));
+        }
     }
 }
 
@@ -203,7 +213,8 @@ __global__ void __launch_bounds__(kSparseThreads) sparse_zero_fill_kernel(const 
     __shared__ int s_found;
 
     const int q = blockIdx.x;
-    const int n_have = A.sign_mode > 0 ? A.st.npos[q] : A.st.nneg[q];
+    // after the final select cnt[q] is the number of positive-score docs kept: all of them when there are < k
+    const int n_have = A.st.cnt[q];
     if (n_have >= A.k || A.sign_mode < 0) return;           // negatives never need zero fill
     const int need = A.k - n_have;
     if (threadIdx.x == 0) {

@@ -13,6 +13,7 @@ Every index covers a contiguous shard [doc_base, doc_base + n_docs) of the corpu
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 from fractions import Fraction
 
@@ -23,7 +24,7 @@ from . import ops
 from ._lib import LEX_BM25, LEX_TFIDF, FusionB200Error
 
 VARIANTS = ("tfidf", "bm25", "atire")
-DEFAULT_TILE_DOCS = 8192
+DEFAULT_TILE_DOCS = int(os.environ.get("FZ_TILE_DOCS", 2048))      # docs per shared-memory accumulator tile
 LONG_LIST_MIN = 512
 
 
