@@ -14,6 +14,7 @@
 #include "ptx.cuh"
 
 #include <cuda.h>
+#include <cstdlib>
 #include <limits>
 
 namespace fz {
@@ -22,13 +23,14 @@ int make_bf16_tile_map(CUtensorMap* map, const void* base, uint64_t rows, uint64
 
 constexpr int kMsDim = 128;                 // embedding dim (two 64-element swizzle rows)
 constexpr int kMsRows = 128;                // UMMA M: query-token rows per tile
-constexpr int kMsChunk = 128;               // doc tokens per MMA (UMMA N <= 128 here), longer docs are chunked
-constexpr int kMsStages = 4;
+constexpr int kMsChunk = 96;                // doc tokens per MMA (UMMA N <= 96 here), longer docs are chunked
+constexpr int kMsStages = 6;                // deep ring: ~20 KB per candidate must cover the HBM latency
 constexpr int kMsABytes = kMsRows * kMsDim * 2;      // 32 KB per query buffer
-constexpr int kMsBBytes = kMsChunk * kMsDim * 2;     // 32 KB per stage
+constexpr int kMsBBytes = kMsChunk * kMsDim * 2;     // 24 KB per stage
 constexpr int kMsTBufs = 4;                           // 4 x 128 TMEM columns
-constexpr int kMsThreads = 256;
-constexpr int kMsBoxes = kMsChunk / 16;               // tensor maps with box heights 16, 32, ..., 128
+constexpr int kMsTCols = 128;                         // TMEM columns per accumulator buffer
+constexpr int kMsThreads = 384;                       // warps 0-3 control, warps 4-7 and 8-11 two epilogue teams
+constexpr int kMsBoxes = kMsChunk / 16;               // tensor maps with box heights 16, 32, ..., 96
 constexpr size_t kMsSmem = 2 * (size_t)kMsABytes + (size_t)kMsStages * kMsBBytes + 1024 + 256;
 
 struct alignas(64) MsMaps {
@@ -41,6 +43,7 @@ struct MsArgs {
     const int64_t* tok_ptr;     // [n_docs + 1]
     long long n_docs, doc_base;
     int n_queries, n_cand, lq;
+    int debug;                  // FZ_MAXSIM_DEBUG: 1 = skip the TMEM read-back, 2 = skip the MMAs (pipeline experiments)
     float* out;                 // [n_queries, n_cand], zero-initialised
 };
 
@@ -167,9 +170,10 @@ __global__ void __launch_bounds__(kMsThreads, 1) maxsim_kernel(const __grid_cons
                             ptx::tc_fence_after();
                             const uint32_t sb = ptx::smem_u32(smem_b + (size_t)stage * kMsBBytes);
                             const uint32_t idesc = ptx::make_idesc_bf16(kMsRows, (uint32_t)R);
-                            const uint32_t d_tmem = tmem_base + tb * kMsChunk;
+                            const uint32_t d_tmem = tmem_base + tb * kMsTCols;
 #pragma unroll
                             for (int k = 0; k < kMsDim / 16; ++k) {
+                                if (M.debug & 2) break;
                                 const int half = k >> 2, kk = k & 3;
                                 const uint64_t da = ptx::make_smem_desc_sw128(sa + half * (kMsABytes / 2) + kk * 32);
                                 const uint64_t db = ptx::make_smem_desc_sw128(sb + half * (R * 128) + kk * 32);
@@ -188,11 +192,15 @@ __global__ void __launch_bounds__(kMsThreads, 1) maxsim_kernel(const __grid_cons
         }
     } else if (warp >= 4) {
         // ===================================== epilogue ==========================================
-        const int ew = warp - 4;
+        // Two teams of four warps (TMEM lane quarter = warp % 4) take alternate candidates, so the TMEM read-back
+        // and the max/sum reduction of one candidate overlap the next candidate's.
+        const int team = (warp - 4) >> 2;
+        const int ew = (warp - 4) & 3;
         const int row = ew * 32 + lane;                 // query token handled by this thread
         const bool row_ok = row < M.lq;
         const bool warp_ok = ew * 32 < M.lq;            // warp has at least one live row
         uint32_t t = 0;
+        uint32_t cand_no = 0;
         for (int q = blockIdx.x; q < M.n_queries; q += gridDim.x) {
             int ns, nl;
             ms_cand_info(M, q, 0, lane, ns, nl);
@@ -203,6 +211,13 @@ __global__ void __launch_bounds__(kMsThreads, 1) maxsim_kernel(const __grid_cons
                 for (int l = 0; l < nb; ++l) {
                     const int len = __shfl_sync(0xffffffffu, cl, l);
                     if (len < 0) continue;
+                    const bool mine = (cand_no++ & 1u) == (uint32_t)team;
+                    const int n_chunks = (len + kMsChunk - 1) / kMsChunk;
+                    if (!mine) {
+                        // stay in phase with every accumulator barrier: a parity wait that skipped a phase would alias
+                        for (int c = 0; c < n_chunks; ++c, ++t) ptx::mbar_wait(&tfull_bar[t % kMsTBufs], (t / kMsTBufs) & 1);
+                        continue;
+                    }
                     float m = -std::numeric_limits<float>::infinity();
                     if (len == 0) m = -9999.f;           // every (padded) doc token is masked to -9999
                     for (int off = 0; off < len; off += kMsChunk, ++t) {
@@ -210,16 +225,20 @@ __global__ void __launch_bounds__(kMsThreads, 1) maxsim_kernel(const __grid_cons
                         const uint32_t tb = t % kMsTBufs;
                         ptx::mbar_wait(&tfull_bar[tb], (t / kMsTBufs) & 1);
                         ptx::tc_fence_after();
-                        if (warp_ok) {
-                            const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + tb * kMsChunk;
-                            for (int cc = 0; cc < n; cc += 16) {
-                                uint32_t r[16];
-                                ptx::tmem_ld_32x16(t_row + cc, r);
-                                ptx::tmem_ld_wait();
+                        if (warp_ok && !(M.debug & 1)) {
+                            const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + tb * kMsTCols;
+                            uint32_t r[kMsChunk / 16][16];
 #pragma unroll
-                                for (int j = 0; j < 16; ++j)
-                                    if (cc + j < n) m = fmaxf(m, __uint_as_float(r[j]));
-                            }
+                            for (int g = 0; g < kMsChunk / 16; ++g)
+                                if (g * 16 < n) ptx::tmem_ld_32x16(t_row + g * 16, r[g]);     // all loads in flight
+                            ptx::tmem_ld_wait();
+#pragma unroll
+                            for (int g = 0; g < kMsChunk / 16; ++g)
+                                if (g * 16 < n) {
+#pragma unroll
+                                    for (int j = 0; j < 16; ++j)
+                                        if (g * 16 + j < n) m = fmaxf(m, __uint_as_float(r[g][j]));
+                                }
                         }
                         ptx::tc_fence_before();
                         __syncwarp();
@@ -274,6 +293,10 @@ extern "C" int fz_maxsim_bf16(const void* q_tok, int lq, const int32_t* cand_ids
     M.n_queries = n_queries;
     M.n_cand = n_cand;
     M.lq = lq;
+    {
+        const char* e = getenv("FZ_MAXSIM_DEBUG");
+        M.debug = e ? atoi(e) : 0;
+    }
     M.out = out_scores;
     const int grid = n_queries < num_sms() ? n_queries : num_sms();
     ProfScope prof("maxsim", stream);
