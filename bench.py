@@ -46,6 +46,8 @@ def parse():
     p.add_argument("--pool", type=int, default=int(os.environ.get("FZ_BENCH_POOL", COLBERT_POOL)))
     p.add_argument("--systems", default=os.environ.get("FZ_BENCH_SYSTEMS", "bm25,dpr,splade,colbert"))
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--ncu-range", action="store_true",
+                   help="bracket ONE extra step with cudaProfilerStart/Stop (use with ncu --profile-from-start off)")
     return p.parse_args()
 
 
@@ -354,6 +356,12 @@ def main():
 
     for _ in range(args.warmup):
         step(q)
+    if args.ncu_range:          # profiler capture range: exactly one step of the hot path, after warm-up
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStart()
+        step(q)
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
     # ---- device-resident timing
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

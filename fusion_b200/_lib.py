@@ -24,8 +24,10 @@ class FusionB200Error(RuntimeError):
 class Postings(C.Structure):
     """mirror of fz_postings_t"""
     _fields_ = [("term_ptr", C.c_void_p), ("post_doc", C.c_void_p), ("post_val", C.c_void_p),
-                ("long_row", C.c_void_p), ("long_tile_off", C.c_void_p), ("n_terms", C.c_int32),
-                ("n_long", C.c_int32), ("n_docs", C.c_int64), ("tile_docs", C.c_int32), ("n_tiles", C.c_int32)]
+                ("short_coarse", C.c_void_p), ("term_slot", C.c_void_p), ("tiled_base", C.c_void_p), ("tiled_tile_off", C.c_void_p),
+                ("tiled_off", C.c_void_p), ("tiled_val", C.c_void_p), ("dense_val", C.c_void_p),
+                ("dense_stride", C.c_int64), ("n_terms", C.c_int32), ("n_tiled", C.c_int32), ("n_dense", C.c_int32),
+                ("tile_docs", C.c_int32), ("n_tiles", C.c_int32), ("n_coarse", C.c_int32), ("n_docs", C.c_int64)]
 
 
 _p, _i, _i64, _sz, _f, _d = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_float, C.c_double
@@ -36,6 +38,7 @@ SIGNATURES = {
     "fz_abi_version": (_i, []),
     "fz_profile_enable": (_i, [_i]),
     "fz_profile_summary": (_i, [C.c_char_p, _sz]),
+    "fz_debug_set_stats": (_i, [_p]),
     "fz_merge_topk_workspace_bytes": (_sz, [_i, _i, _i]),
     "fz_merge_topk_f32": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p, _sz, _p]),
     "fz_merge_topk_f64": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p, _sz, _p]),
@@ -45,7 +48,6 @@ SIGNATURES = {
     "fz_fuse_workspace_bytes": (_sz, [_i, _i, _p]),
     "fz_fuse": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _i, _p, _sz, _p]),
     "fz_lexical_impacts": (_i, [_p, _p, _p, _p, _p, C.c_int32, _i64, _d, _d, _d, _i, _p, _p]),
-    "fz_long_tile_offsets": (_i, [_p, _p, _p, C.c_int32, C.c_int32, C.c_int32, _p, _p]),
     "fz_sparse_topk_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "fz_sparse_topk_f64": (_i, [_p, _p, _p, _i, _i, _i64, _i, _i, _i, _p, _p, _p, _p, _sz, _p]),
     "fz_sparse_topk_f32": (_i, [_p, _p, _p, _p, _i, _i, _i64, _i, _i, _i, _p, _p, _p, _p, _sz, _p]),
@@ -55,7 +57,8 @@ SIGNATURES = {
     "fz_dense_topk": (_i, [_p, _p, _p, _p, _i, _i64, _i, _i, _f, _i64, _i, _i, _p, _p, _p, _p, _sz, _p]),
     "fz_dense_scores_f32": (_i, [_p, _p, _i, _i64, _i, _p, _p]),
     "fz_normalize_rows": (_i, [_p, _i64, _i, _i, _p, _p, _p]),
-    "fz_maxsim_bf16": (_i, [_p, _i, _p, _p, _p, _i64, _i64, _i64, _i, _i, _p, _p]),
+    "fz_maxsim_workspace_bytes": (_sz, [_i, _i]),
+    "fz_maxsim_bf16": (_i, [_p, _i, _p, _p, _p, _i64, _i64, _i64, _i, _i, _p, _p, _sz, _p]),
 }
 
 _lib = None

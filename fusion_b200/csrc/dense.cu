@@ -22,6 +22,8 @@
 
 namespace fz {
 
+extern void* g_debug_stats;
+
 // ----------------------------------------------------------------------------------- tensor maps
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -63,7 +65,7 @@ constexpr int kStages = 4;
 constexpr int kABytes = kBM * kBK * 2;   // 16 KB
 constexpr int kBBytes = kBN * kBK * 2;   // 32 KB
 constexpr int kStageBytes = kABytes + kBBytes;
-constexpr int kGemmThreads = 256;        // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps4-7 epilogue
+constexpr int kGemmThreads = 384;        // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps 4-7 / 8-11 two epilogue teams
 constexpr int kTmemCols = 512;           // two 256-column fp32 accumulators
 constexpr size_t kGemmSmem = (size_t)kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 
@@ -73,6 +75,7 @@ struct GemmArgs {
     int num_k_blocks;
     int m_tiles, n_tiles;
     CandState<float> st;
+    unsigned long long* stats;   // optional [gridDim.x, 8] cycle counters (fz_debug_set_stats)
 };
 
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -120,12 +123,15 @@ dense_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         if (ptx::elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
+            long long st_wait_empty = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int n_t = tile / G.m_tiles, m_t = tile - n_t * G.m_tiles;
                 const int q0 = m_t * kBM;
                 const long long d0 = G.r_lo + (long long)n_t * kBN;
                 for (int kb = 0; kb < G.num_k_blocks; ++kb) {
+                    const long long t0 = clock64();
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    st_wait_empty += clock64() - t0;
                     unsigned char* sa = smem + (size_t)stage * kStageBytes;
                     ptx::mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
                     ptx::tma_load_2d(sa, &tmap_q, &full_bar[stage], kb * kBK, q0);
@@ -133,6 +139,7 @@ dense_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
+            if (G.stats) G.stats[blockIdx.x * 8 + 0] += (unsigned long long)st_wait_empty;
         }
     } else if (warp == 1) {
         // ================================ MMA issuer (one elected lane) ===================================
@@ -141,13 +148,19 @@ dense_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
+            long long st_wait_tempty = 0, st_wait_full = 0, st_issue = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
                 const int buf = it & 1;
+                const long long t0 = clock64();
                 ptx::mbar_wait(&tempty_bar[buf], ((it >> 1) & 1) ^ 1);   // epilogue drained this accumulator
+                st_wait_tempty += clock64() - t0;
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)buf * kBN;
                 for (int kb = 0; kb < G.num_k_blocks; ++kb) {
+                    const long long t1 = clock64();
                     ptx::mbar_wait(&full_bar[stage], phase);
+                    const long long t2 = clock64();
+                    st_wait_full += t2 - t1;
                     ptx::tc_fence_after();
                     const uint32_t sa = ptx::smem_u32(smem + (size_t)stage * kStageBytes);
                     const uint32_t sb = sa + kABytes;
@@ -158,56 +171,118 @@ dense_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                         ptx::mma_bf16_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
                     ptx::mma_commit(&empty_bar[stage]);     // smem stage reusable once these MMAs retire
+                    st_issue += clock64() - t2;
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
                 ptx::mma_commit(&tfull_bar[buf]);           // accumulator complete
             }
+            if (G.stats) {
+                G.stats[blockIdx.x * 8 + 1] += (unsigned long long)st_wait_tempty;
+                G.stats[blockIdx.x * 8 + 2] += (unsigned long long)st_wait_full;
+                G.stats[blockIdx.x * 8 + 3] += (unsigned long long)st_issue;
+            }
         }
     } else if (warp >= 4) {
         // ================================ epilogue: TMEM -> threshold filter -> candidate append ==========
-        const int ew = warp - 4;                            // == warp % 4: the TMEM lane quarter this warp may read
-        int it = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        // Two teams of four warps: team t owns accumulator buffer t, i.e. every other tile of this CTA, so the candidate
+        // appends of one tile (an atomic round trip per thread) overlap the read-back of the next.
+        const int ew = (warp - 4) & 3;                      // == warp % 4: the TMEM lane quarter this warp may read
+        const int team = (warp - 4) >> 2;
+        int it = team;
+        long long st_wait_tfull = 0, st_pass2 = 0, st_pass2_n = 0;
+        const long long st_begin = clock64();
+        // Every global load on this path is issued one tile ahead: under a saturated memory system a demand load
+        // takes thousands of cycles and would otherwise sit between "accumulator ready" and "accumulator released".
+        auto tau_of = [&](int tile) {
+            if (tile >= total_tiles) return std::numeric_limits<float>::infinity();
+            const int n_t = tile / G.m_tiles, m_t = tile - n_t * G.m_tiles;
+            const int q = m_t * kBM + ew * 32 + lane;
+            return q < G.n_queries ? G.st.tau[q] : std::numeric_limits<float>::infinity();
+        };
+        float tau_next = tau_of(blockIdx.x + team * gridDim.x);
+        for (int tile = blockIdx.x + team * gridDim.x; tile < total_tiles; tile += 2 * gridDim.x, it += 2) {
             const int n_t = tile / G.m_tiles, m_t = tile - n_t * G.m_tiles;
             const int buf = it & 1;
             const int q = m_t * kBM + ew * 32 + lane;
             const long long d0 = G.r_lo + (long long)n_t * kBN;
             const int limit = (int)min((long long)kBN, G.r_hi - d0);
-            const bool q_ok = q < G.n_queries;
-            const float tau = q_ok ? G.st.tau[q] : std::numeric_limits<float>::infinity();
+            const float tau = tau_next;
+            tau_next = tau_of(tile + 2 * gridDim.x);
+            const long long t0 = clock64();
             ptx::mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
+            st_wait_tfull += clock64() - t0;
             ptx::tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)buf * kBN;
-#pragma unroll 1
+            // Pass 1: each 32-column chunk is reduced with a max TREE (no dependent chain) while the next chunk's
+            // tcgen05.ld is already in flight; only a chunk whose maximum beats tau pays for the compare mask.
+            uint32_t ra[32], rb[32];
+            uint32_t flags = 0;
+            int total = 0;
+            ptx::tmem_ld_32x32(t_row, ra);
+#pragma unroll
             for (int c = 0; c < kBN / 32; ++c) {
-                uint32_t r[32];
-                ptx::tmem_ld_32x32(t_row + c * 32, r);
-                ptx::tmem_ld_wait();
-                uint32_t mask = 0;
+                uint32_t(&cur)[32] = (c & 1) ? rb : ra;
+                ptx::tmem_ld_wait(cur);
+                if (c + 1 < kBN / 32) ptx::tmem_ld_32x32(t_row + (c + 1) * 32, (c & 1) ? ra : rb);
+                float m8[8];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float v = __uint_as_float(r[j]);
-                    if (v > tau && c * 32 + j < limit) mask |= 1u << j;
+                for (int j = 0; j < 8; ++j)
+                    m8[j] = fmaxf(fmaxf(__uint_as_float(cur[j]), __uint_as_float(cur[j + 8])),
+                                  fmaxf(__uint_as_float(cur[j + 16]), __uint_as_float(cur[j + 24])));
+                const float mx = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])),
+                                       fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
+                if (mx > tau) {
+                    uint32_t mask = 0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (__uint_as_float(cur[j]) > tau && c * 32 + j < limit) mask |= 1u << j;
+                    if (mask) {
+                        flags |= 1u << c;
+                        total += __popc(mask);
+                    }
                 }
-                if (mask) {
-                    const int cnt = __popc(mask);
-                    int base = atomicAdd(&G.st.cnt[q], cnt);
-                    const size_t off = (size_t)q * G.st.cap;
+            }
+            // Pass 2: one atomic per thread and tile reserves the slots and the flagged chunks are read again.
+            // tcgen05.ld is warp-collective, so the chunk loop runs over the warp-wide union of the flags.
+            // (Parking the survivors in shared memory to release the accumulator before the atomic round trip was
+            // measured SLOWER: the kernel is bound by L2 -> SM operand traffic, and a team cannot start its next tile
+            // before its appends have drained anyway.)
+            const uint32_t wflags = __reduce_or_sync(0xffffffffu, flags);
+            const long long tp2 = clock64();
+            if (wflags) {
+                int base = total > 0 ? atomicAdd(&G.st.cnt[q], total) : 0;
+                const size_t off = (size_t)q * G.st.cap;
+#pragma unroll 1
+                for (int c = 0; c < kBN / 32; ++c) {
+                    if (!(wflags & (1u << c))) continue;
+                    ptx::tmem_ld_32x32(t_row + c * 32, ra);
+                    ptx::tmem_ld_wait(ra);
+                    if (flags & (1u << c)) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        if (mask & (1u << j)) {
-                            if (base < G.st.cap) {
-                                G.st.score[off + base] = __uint_as_float(r[j]);
-                                G.st.id[off + base] = (int32_t)(d0 + c * 32 + j);
+                        for (int j = 0; j < 32; ++j) {
+                            const float v = __uint_as_float(ra[j]);
+                            if (v > tau && c * 32 + j < limit) {
+                                if (base < G.st.cap) {
+                                    G.st.score[off + base] = v;
+                                    G.st.id[off + base] = (int32_t)(d0 + c * 32 + j);
+                                }
+                                ++base;
                             }
-                            ++base;
                         }
                     }
                 }
+                st_pass2 += clock64() - tp2;
+                ++st_pass2_n;
             }
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&tempty_bar[buf]);
+        }
+        if (G.stats && ew == 0 && lane == 0 && team == 0) {
+            G.stats[blockIdx.x * 8 + 4] += (unsigned long long)st_wait_tfull;
+            G.stats[blockIdx.x * 8 + 5] += (unsigned long long)(clock64() - st_begin);
+            G.stats[blockIdx.x * 8 + 6] += (unsigned long long)st_pass2;
+            G.stats[blockIdx.x * 8 + 7] += (unsigned long long)st_pass2_n;
         }
     }
     ptx::tc_fence_before();
@@ -353,6 +428,7 @@ int fz_dense_topk(const void* q_bf16, const void* d_bf16, const float* q_f32, co
     G.num_k_blocks = dim / kBK;
     G.m_tiles = ceil_div(n_queries, kBM);
     G.st = cand_state_carve<float>(ws, n_queries, cap, out_status);
+    G.stats = (unsigned long long*)g_debug_stats;
     rc = cand_init<float>(G.st, n_queries, stream);
     if (rc) return rc;
 

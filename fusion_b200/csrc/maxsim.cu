@@ -4,34 +4,34 @@
 //   src/utils/colbert_ir.py:245-255, src/retrievers/hybrid.py:109-137)
 //
 // Layout: the UMMA A operand is the query's token matrix (rows = query tokens -> TMEM lanes), the B operand is a
-// candidate document's token block (rows = doc tokens -> TMEM columns), K = 128 embedding dims.  The max over doc
-// tokens is then a per-thread running max over the columns each epilogue thread reads back with tcgen05.ld, and the
-// sum over query tokens one warp reduction per candidate.  A persistent CTA owns whole queries: warp 0 streams the
-// candidates' token rows with TMA (one 2-D box per 64-dim half, box height = the doc length rounded up to 16, so a
-// 70-token passage moves 80 rows), warp 1 issues the MMAs, warps 4-7 reduce.  The kernel is HBM-bound: 2*Lq = 128
-// FLOP per bf16 element read.
+// GROUP of candidate documents' token blocks packed back to back (rows = doc tokens -> TMEM columns, up to 256 per
+// MMA), K = 128 embedding dims.  The max over doc tokens is then a per-thread running max over the columns each
+// epilogue thread reads back with tcgen05.ld, and the sum over query tokens one warp reduction per candidate.
+// A persistent CTA owns whole queries: warp 0 streams the candidates' token rows with TMA (one 2-D box per 64-dim
+// half and candidate, box height = the doc length rounded up to 16, so a 70-token passage moves 80 rows) into a
+// 3-stage ring of 64 KB groups, warp 1 issues 8 MMAs per group into one of two 256-column TMEM accumulators, two
+// teams of epilogue warps reduce alternate groups.  Packing ~3 passages per group amortises the barrier round
+// trips and the shared-memory reads of the query operand.  The kernel is HBM-bound: 2*Lq = 128 FLOP per bf16
+// element read.
 #include "common.cuh"
 #include "ptx.cuh"
 
 #include <cuda.h>
-#include <cstdlib>
 #include <limits>
 
 namespace fz {
 
 int make_bf16_tile_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows);
+extern void* g_debug_stats;
 
 constexpr int kMsDim = 128;                 // embedding dim (two 64-element swizzle rows)
 constexpr int kMsRows = 128;                // UMMA M: query-token rows per tile
-constexpr int kMsChunk = 96;                // doc tokens per MMA (UMMA N <= 96 here), longer docs are chunked
-constexpr int kMsStages = 6;                // deep ring: ~20 KB per candidate must cover the HBM latency
-constexpr int kMsABytes = kMsRows * kMsDim * 2;      // 32 KB per query buffer
-constexpr int kMsBBytes = kMsChunk * kMsDim * 2;     // 24 KB per stage
-constexpr int kMsTBufs = 4;                           // 4 x 128 TMEM columns
-constexpr int kMsTCols = 128;                         // TMEM columns per accumulator buffer
-constexpr int kMsThreads = 384;                       // warps 0-3 control, warps 4-7 and 8-11 two epilogue teams
-constexpr int kMsBoxes = kMsChunk / 16;               // tensor maps with box heights 16, 32, ..., 96
-constexpr size_t kMsSmem = 2 * (size_t)kMsABytes + (size_t)kMsStages * kMsBBytes + 1024 + 256;
+constexpr int kMsGroupMax = 256;            // doc-token rows per MMA group (UMMA N <= 256)
+constexpr int kMsStages = 3;
+constexpr int kMsTBufs = 2;                 // 2 x 256 TMEM columns
+constexpr int kMsThreads = 384;             // warps 0-3 control, warps 4-7 and 8-11 two epilogue teams
+constexpr int kMsBoxes = kMsGroupMax / 16;  // tensor maps with box heights 16, 32, ..., 256
+constexpr size_t kMsSmemMax = 227 * 1024;
 
 struct alignas(64) MsMaps {
     CUtensorMap q;
@@ -39,35 +39,82 @@ struct alignas(64) MsMaps {
 };
 
 struct MsArgs {
-    const int32_t* cand;        // [n_queries, n_cand] global doc ids
-    const int64_t* tok_ptr;     // [n_docs + 1]
-    long long n_docs, doc_base;
+    const int2* info;           // [n_queries, n_cand] (first token row, token count | -1 = not in this shard)
     int n_queries, n_cand, lq;
-    int debug;                  // FZ_MAXSIM_DEBUG: 1 = skip the TMEM read-back, 2 = skip the MMAs (pipeline experiments)
+    int a_rows;                 // query rows held in shared memory per 64-dim half (lq rounded up to 8)
+    int group_rows;             // doc-token rows per stage (multiple of 16, <= 256)
     float* out;                 // [n_queries, n_cand], zero-initialised
+    unsigned long long* stats;  // optional [gridDim.x, 8] cycle counters (fz_debug_set_stats), NULL = off
 };
 
-// (start row, token count) of candidate c0 + lane of query q; len -1 = not in this shard
-__device__ __forceinline__ void ms_cand_info(const MsArgs& M, int q, int c0, int lane, int& start, int& len) {
-    start = 0;
-    len = -1;
+// (start row, token count) of every (query, candidate) pair, gathered once by a pre-pass: under a saturated memory
+// system a demand load takes thousands of cycles, so the persistent kernel must not chase cand -> tok_ptr -> tokens
+// pointers on its critical path.  len -1 = candidate outside this shard.
+__global__ void maxsim_info_kernel(const int32_t* __restrict__ cand, const int64_t* __restrict__ tok_ptr, long long n_docs,
+                                   long long doc_base, long long n_pairs, int2* __restrict__ info) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_pairs; i += (long long)gridDim.x * blockDim.x) {
+        const long long d = (long long)cand[i] - doc_base;
+        int2 v = make_int2(0, -1);
+        if (d >= 0 && d < n_docs) {
+            const long long s = tok_ptr[d], e = tok_ptr[d + 1];
+            v = make_int2((int)s, (int)(e - s));
+        }
+        info[i] = v;
+    }
+}
+
+__device__ __forceinline__ int2 ms_cand_info(const MsArgs& M, int q, int c0, int lane) {
     const int c = c0 + lane;
-    if (c < M.n_cand) {
-        const long long d = (long long)M.cand[(size_t)q * M.n_cand + c] - M.doc_base;
-        if (d >= 0 && d < M.n_docs) {
-            const long long s = M.tok_ptr[d], e = M.tok_ptr[d + 1];
-            start = (int)s;
-            len = (int)(e - s);
+    return c < M.n_cand ? __ldg(&M.info[(size_t)q * M.n_cand + c]) : make_int2(0, -1);
+}
+
+// Walk query q's candidates and cut them into pieces (<= group_rows tokens) packed greedily into groups.  Every role
+// (producer, MMA issuer, both epilogue teams) runs this same warp-uniform walk, so they agree on the packing without
+// exchanging anything.
+//   on_piece(c, start_row, n, R, col, first_of_cand, last_of_cand, first_of_group)
+//   on_group_end(rows)           rows = columns of the group (multiple of 16)
+//   on_empty(c)                  candidate with zero tokens
+template <class FP, class FG, class FE>
+__device__ __forceinline__ void ms_walk(const MsArgs& M, int q, int lane, FP on_piece, FG on_group_end, FE on_empty) {
+    int rows = 0;
+    int2 i1 = ms_cand_info(M, q, 0, lane), i2 = ms_cand_info(M, q, 32, lane);   // two blocks of 32 in flight
+    for (int c0 = 0; c0 < M.n_cand; c0 += 32) {
+        const int2 cur = i1;
+        i1 = i2;
+        i2 = ms_cand_info(M, q, c0 + 64, lane);
+        const int nb = min(32, M.n_cand - c0);
+        for (int l = 0; l < nb; ++l) {
+            const int start = __shfl_sync(0xffffffffu, cur.x, l);
+            const int len = __shfl_sync(0xffffffffu, cur.y, l);
+            if (len <= 0) {
+                if (len == 0) on_empty(c0 + l);
+                continue;
+            }
+            for (int off = 0; off < len; off += M.group_rows) {
+                const int n = min(M.group_rows, len - off);
+                const int R = (n + 15) & ~15;
+                if (rows + R > M.group_rows) {
+                    on_group_end(rows);
+                    rows = 0;
+                }
+                on_piece(c0 + l, start + off, n, R, rows, off == 0, off + n >= len, rows == 0);
+                rows += R;
+            }
         }
     }
+    if (rows > 0) on_group_end(rows);
 }
 
 __global__ void __launch_bounds__(kMsThreads, 1) maxsim_kernel(const __grid_constant__ MsMaps maps, const MsArgs M) {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
-    unsigned char* smem_a = smem;                                  // 2 query buffers
-    unsigned char* smem_b = smem + 2 * (size_t)kMsABytes;          // kMsStages doc-chunk stages
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + (size_t)kMsStages * kMsBBytes);
+    const int a_half = M.a_rows * 128;                              // bytes of one 64-dim half of the query operand
+    const int a_bytes = (2 * a_half + 1023) & ~1023;
+    const int b_half = M.group_rows * 128;
+    const int b_bytes = 2 * b_half;                                 // multiple of 4096
+    unsigned char* smem_a = smem;                                   // 2 query buffers
+    unsigned char* smem_b = smem + 2 * (size_t)a_bytes;             // kMsStages doc-group stages
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + (size_t)kMsStages * b_bytes);
     uint64_t* full_bar = bars;                          // [kMsStages]
     uint64_t* empty_bar = full_bar + kMsStages;         // [kMsStages]
     uint64_t* afull_bar = empty_bar + kMsStages;        // [2]
@@ -77,6 +124,7 @@ __global__ void __launch_bounds__(kMsThreads, 1) maxsim_kernel(const __grid_cons
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + kMsTBufs);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int live_warps = (M.lq + 31) >> 5;            // epilogue warps per team that own query rows
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&maps.q);
@@ -85,7 +133,8 @@ __global__ void __launch_bounds__(kMsThreads, 1) maxsim_kernel(const __grid_cons
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < kMsStages; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 1); }
         for (int i = 0; i < 2; ++i) { ptx::mbar_init(&afull_bar[i], 1); ptx::mbar_init(&aempty_bar[i], 1); }
-        for (int i = 0; i < kMsTBufs; ++i) { ptx::mbar_init(&tfull_bar[i], 1); ptx::mbar_init(&tempty_bar[i], 4); }
+        // both teams pass every accumulator (the owner after reading it), so a waiter can never fall a phase behind
+        for (int i = 0; i < kMsTBufs; ++i) { ptx::mbar_init(&tfull_bar[i], 1); ptx::mbar_init(&tempty_bar[i], 2 * live_warps); }
         ptx::fence_barrier_init();
     }
     if (warp == 2) {
@@ -99,6 +148,7 @@ __global__ void __launch_bounds__(kMsThreads, 1) maxsim_kernel(const __grid_cons
 
     if (warp == 0) {
         // ===================================== TMA producer =====================================
+        long long st_wait_empty = 0;
         int stage = 0;
         uint32_t phase = 0;
         int qi = 0;
@@ -106,44 +156,43 @@ __global__ void __launch_bounds__(kMsThreads, 1) maxsim_kernel(const __grid_cons
             const int abuf = qi & 1;
             if (lane == 0) {
                 ptx::mbar_wait(&aempty_bar[abuf], ((qi >> 1) & 1) ^ 1);
-                unsigned char* sa = smem_a + (size_t)abuf * kMsABytes;
-                ptx::mbar_arrive_expect_tx(&afull_bar[abuf], kMsABytes);
+                unsigned char* sa = smem_a + (size_t)abuf * a_bytes;
+                ptx::mbar_arrive_expect_tx(&afull_bar[abuf], 2 * a_half);
                 ptx::tma_load_2d(sa, &maps.q, &afull_bar[abuf], 0, q * M.lq);
-                ptx::tma_load_2d(sa + kMsABytes / 2, &maps.q, &afull_bar[abuf], 64, q * M.lq);
+                ptx::tma_load_2d(sa + a_half, &maps.q, &afull_bar[abuf], 64, q * M.lq);
             }
             __syncwarp();
-            int ns, nl;
-            ms_cand_info(M, q, 0, lane, ns, nl);
-            for (int c0 = 0; c0 < M.n_cand; c0 += 32) {
-                const int cs = ns, cl = nl;
-                if (c0 + 32 < M.n_cand) ms_cand_info(M, q, c0 + 32, lane, ns, nl);
-                const int nb = min(32, M.n_cand - c0);
-                for (int l = 0; l < nb; ++l) {
-                    const int start = __shfl_sync(0xffffffffu, cs, l);
-                    const int len = __shfl_sync(0xffffffffu, cl, l);
-                    for (int off = 0; off < len; off += kMsChunk) {
-                        const int n = min(kMsChunk, len - off);
-                        const int R = (n + 15) & ~15;
-                        if (lane == 0) {
+            ms_walk(M, q, lane,
+                [&](int, int row0, int, int R, int col, bool, bool, bool first_of_group) {
+                    if (lane == 0) {
+                        if (first_of_group) {
+                            const long long t0 = clock64();
                             ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-                            unsigned char* sb = smem_b + (size_t)stage * kMsBBytes;
-                            const CUtensorMap* mp = &maps.d[R / 16 - 1];
-                            ptx::mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)R * kMsDim * 2);
-                            ptx::tma_load_2d(sb, mp, &full_bar[stage], 0, start + off);
-                            ptx::tma_load_2d(sb + (size_t)R * 128, mp, &full_bar[stage], 64, start + off);
+                            st_wait_empty += clock64() - t0;
                         }
-                        __syncwarp();
-                        if (++stage == kMsStages) { stage = 0; phase ^= 1; }
+                        unsigned char* sb = smem_b + (size_t)stage * b_bytes + (size_t)col * 128;
+                        const CUtensorMap* mp = &maps.d[R / 16 - 1];
+                        ptx::mbar_expect_tx(&full_bar[stage], (uint32_t)R * kMsDim * 2);
+                        ptx::tma_load_2d(sb, mp, &full_bar[stage], 0, row0);
+                        ptx::tma_load_2d(sb + b_half, mp, &full_bar[stage], 64, row0);
                     }
-                }
-            }
+                    __syncwarp();
+                },
+                [&](int) {
+                    if (lane == 0) ptx::mbar_arrive(&full_bar[stage]);
+                    __syncwarp();
+                    if (++stage == kMsStages) { stage = 0; phase ^= 1; }
+                },
+                [&](int) {});
         }
+        if (M.stats && lane == 0) M.stats[blockIdx.x * 8 + 0] = (unsigned long long)st_wait_empty;
     } else if (warp == 1) {
         // ===================================== MMA issuer =======================================
+        long long st_wait_tempty = 0, st_wait_full = 0, st_issue = 0;
         int stage = 0;
         uint32_t phase = 0;
         int qi = 0;
-        uint32_t t = 0;     // chunk counter -> TMEM buffer
+        uint32_t g = 0;     // group counter -> TMEM buffer
         for (int q = blockIdx.x; q < M.n_queries; q += gridDim.x, ++qi) {
             const int abuf = qi & 1;
             if (lane == 0) {
@@ -151,103 +200,139 @@ __global__ void __launch_bounds__(kMsThreads, 1) maxsim_kernel(const __grid_cons
                 ptx::tc_fence_after();
             }
             __syncwarp();
-            const uint32_t sa = ptx::smem_u32(smem_a + (size_t)abuf * kMsABytes);
-            int ns, nl;
-            ms_cand_info(M, q, 0, lane, ns, nl);
-            for (int c0 = 0; c0 < M.n_cand; c0 += 32) {
-                const int cl = nl;
-                if (c0 + 32 < M.n_cand) ms_cand_info(M, q, c0 + 32, lane, ns, nl);
-                const int nb = min(32, M.n_cand - c0);
-                for (int l = 0; l < nb; ++l) {
-                    const int len = __shfl_sync(0xffffffffu, cl, l);
-                    for (int off = 0; off < len; off += kMsChunk, ++t) {
-                        const int n = min(kMsChunk, len - off);
-                        const int R = (n + 15) & ~15;
-                        if (lane == 0) {
-                            const uint32_t tb = t % kMsTBufs;
-                            ptx::mbar_wait(&tempty_bar[tb], ((t / kMsTBufs) & 1) ^ 1);
-                            ptx::mbar_wait(&full_bar[stage], phase);
-                            ptx::tc_fence_after();
-                            const uint32_t sb = ptx::smem_u32(smem_b + (size_t)stage * kMsBBytes);
-                            const uint32_t idesc = ptx::make_idesc_bf16(kMsRows, (uint32_t)R);
-                            const uint32_t d_tmem = tmem_base + tb * kMsTCols;
+            const uint32_t sa = ptx::smem_u32(smem_a + (size_t)abuf * a_bytes);
+            ms_walk(M, q, lane,
+                [&](int, int, int, int, int, bool, bool, bool) {},
+                [&](int rows) {
+                    if (lane == 0) {
+                        const uint32_t tb = g % kMsTBufs;
+                        const long long t0 = clock64();
+                        ptx::mbar_wait(&tempty_bar[tb], ((g / kMsTBufs) & 1) ^ 1);
+                        const long long t1 = clock64();
+                        ptx::mbar_wait(&full_bar[stage], phase);
+                        const long long t2 = clock64();
+                        st_wait_tempty += t1 - t0;
+                        st_wait_full += t2 - t1;
+                        ptx::tc_fence_after();
+                        const uint32_t sb = ptx::smem_u32(smem_b + (size_t)stage * b_bytes);
+                        const uint32_t idesc = ptx::make_idesc_bf16(kMsRows, (uint32_t)rows);
+                        const uint32_t d_tmem = tmem_base + tb * kMsGroupMax;
 #pragma unroll
-                            for (int k = 0; k < kMsDim / 16; ++k) {
-                                if (M.debug & 2) break;
-                                const int half = k >> 2, kk = k & 3;
-                                const uint64_t da = ptx::make_smem_desc_sw128(sa + half * (kMsABytes / 2) + kk * 32);
-                                const uint64_t db = ptx::make_smem_desc_sw128(sb + half * (R * 128) + kk * 32);
-                                ptx::mma_bf16_ss(d_tmem, da, db, idesc, k != 0 ? 1u : 0u);
-                            }
-                            ptx::mma_commit(&empty_bar[stage]);
-                            ptx::mma_commit(&tfull_bar[tb]);
+                        for (int k = 0; k < kMsDim / 16; ++k) {
+                            const int half = k >> 2, kk = k & 3;
+                            const uint64_t da = ptx::make_smem_desc_sw128(sa + half * a_half + kk * 32);
+                            const uint64_t db = ptx::make_smem_desc_sw128(sb + half * b_half + kk * 32);
+                            ptx::mma_bf16_ss(d_tmem, da, db, idesc, k != 0 ? 1u : 0u);
                         }
-                        __syncwarp();
-                        if (++stage == kMsStages) { stage = 0; phase ^= 1; }
+                        ptx::mma_commit(&empty_bar[stage]);
+                        ptx::mma_commit(&tfull_bar[tb]);
+                        st_issue += clock64() - t2;
                     }
-                }
-            }
+                    __syncwarp();
+                    ++g;
+                    if (++stage == kMsStages) { stage = 0; phase ^= 1; }
+                },
+                [&](int) {});
             if (lane == 0) ptx::mma_commit(&aempty_bar[abuf]);   // query buffer free once its last MMA retires
             __syncwarp();
         }
+        if (M.stats && lane == 0) {
+            M.stats[blockIdx.x * 8 + 1] = (unsigned long long)st_wait_tempty;
+            M.stats[blockIdx.x * 8 + 2] = (unsigned long long)st_wait_full;
+            M.stats[blockIdx.x * 8 + 3] = (unsigned long long)st_issue;
+        }
     } else if (warp >= 4) {
         // ===================================== epilogue ==========================================
-        // Two teams of four warps (TMEM lane quarter = warp % 4) take alternate candidates, so the TMEM read-back
-        // and the max/sum reduction of one candidate overlap the next candidate's.
+        // Two teams of four warps (TMEM lane quarter = warp % 4) take alternate groups, so the TMEM read-back and the
+        // max/sum reduction of one group overlap the next group's.  A passage longer than one group keeps its team.
         const int team = (warp - 4) >> 2;
         const int ew = (warp - 4) & 3;
-        const int row = ew * 32 + lane;                 // query token handled by this thread
-        const bool row_ok = row < M.lq;
-        const bool warp_ok = ew * 32 < M.lq;            // warp has at least one live row
-        uint32_t t = 0;
-        uint32_t cand_no = 0;
-        for (int q = blockIdx.x; q < M.n_queries; q += gridDim.x) {
-            int ns, nl;
-            ms_cand_info(M, q, 0, lane, ns, nl);
-            for (int c0 = 0; c0 < M.n_cand; c0 += 32) {
-                const int cl = nl;
-                if (c0 + 32 < M.n_cand) ms_cand_info(M, q, c0 + 32, lane, ns, nl);
-                const int nb = min(32, M.n_cand - c0);
-                for (int l = 0; l < nb; ++l) {
-                    const int len = __shfl_sync(0xffffffffu, cl, l);
-                    if (len < 0) continue;
-                    const bool mine = (cand_no++ & 1u) == (uint32_t)team;
-                    const int n_chunks = (len + kMsChunk - 1) / kMsChunk;
-                    if (!mine) {
-                        // stay in phase with every accumulator barrier: a parity wait that skipped a phase would alias
-                        for (int c = 0; c < n_chunks; ++c, ++t) ptx::mbar_wait(&tfull_bar[t % kMsTBufs], (t / kMsTBufs) & 1);
-                        continue;
-                    }
-                    float m = -std::numeric_limits<float>::infinity();
-                    if (len == 0) m = -9999.f;           // every (padded) doc token is masked to -9999
-                    for (int off = 0; off < len; off += kMsChunk, ++t) {
-                        const int n = min(kMsChunk, len - off);
-                        const uint32_t tb = t % kMsTBufs;
-                        ptx::mbar_wait(&tfull_bar[tb], (t / kMsTBufs) & 1);
-                        ptx::tc_fence_after();
-                        if (warp_ok && !(M.debug & 1)) {
-                            const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + tb * kMsTCols;
-                            uint32_t r[kMsChunk / 16][16];
-#pragma unroll
-                            for (int g = 0; g < kMsChunk / 16; ++g)
-                                if (g * 16 < n) ptx::tmem_ld_32x16(t_row + g * 16, r[g]);     // all loads in flight
-                            ptx::tmem_ld_wait();
-#pragma unroll
-                            for (int g = 0; g < kMsChunk / 16; ++g)
-                                if (g * 16 < n) {
-#pragma unroll
-                                    for (int j = 0; j < 16; ++j)
-                                        if (g * 16 + j < n) m = fmaxf(m, __uint_as_float(r[g][j]));
-                                }
+        if (ew < live_warps) {
+            const int row = ew * 32 + lane;                 // query token handled by this thread
+            const bool row_ok = row < M.lq;
+            uint32_t g = 0;
+            int owner = 0;
+            float m = -std::numeric_limits<float>::infinity();
+            long long st_wait_tfull = 0, st_tmem = 0, st_sum = 0;
+            const long long st_begin = clock64();
+            for (int q = blockIdx.x; q < M.n_queries; q += gridDim.x) {
+                ms_walk(M, q, lane,
+                    [&](int c, int, int n, int, int col, bool first_of_cand, bool last_of_cand, bool first_of_group) {
+                        const uint32_t tb = g % kMsTBufs;
+                        if (first_of_group) {
+                            const long long t0 = clock64();
+                            ptx::mbar_wait(&tfull_bar[tb], (g / kMsTBufs) & 1);
+                            st_wait_tfull += clock64() - t0;
+                            ptx::tc_fence_after();
                         }
+                        if (first_of_cand) owner ^= 1;          // passages alternate between the teams; a continuation
+                        if (owner != team) return;              // piece stays with the team that holds its running max
+                        const long long tq0 = clock64();
+                        const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + tb * kMsGroupMax + (uint32_t)col;
+                        // 96 columns per step (a whole passage, usually): every tcgen05.ld in flight before the one wait,
+                        // four independent max chains.  A 32-column load is used only where the 16-rounded piece covers
+                        // it, so no load runs past the accumulator.
+                        float m0 = m, m1 = m, m2 = m, m3 = m;
+                        auto load = [&](uint32_t (&r)[32], int c, int rem) {
+                            if (rem > 16) ptx::tmem_ld_32x32(t_row + c, r); else if (rem > 0) ptx::tmem_ld_32x16_lo(t_row + c, r);
+                        };
+                        auto reduce = [&](const uint32_t (&r)[32], int rem) {
+                            if (rem >= 32) {
+#pragma unroll
+                                for (int j = 0; j < 32; j += 4) {
+                                    m0 = fmaxf(m0, __uint_as_float(r[j]));
+                                    m1 = fmaxf(m1, __uint_as_float(r[j + 1]));
+                                    m2 = fmaxf(m2, __uint_as_float(r[j + 2]));
+                                    m3 = fmaxf(m3, __uint_as_float(r[j + 3]));
+                                }
+                            } else if (rem > 0) {
+#pragma unroll
+                                for (int j = 0; j < 32; j += 4) {
+                                    if (j < rem) m0 = fmaxf(m0, __uint_as_float(r[j]));
+                                    if (j + 1 < rem) m1 = fmaxf(m1, __uint_as_float(r[j + 1]));
+                                    if (j + 2 < rem) m2 = fmaxf(m2, __uint_as_float(r[j + 2]));
+                                    if (j + 3 < rem) m3 = fmaxf(m3, __uint_as_float(r[j + 3]));
+                                }
+                            }
+                        };
+                        for (int c0 = 0; c0 < n; c0 += 96) {
+                            uint32_t ra[32], rb[32], rc[32];
+                            const int rem = n - c0;
+                            load(ra, c0, rem);
+                            load(rb, c0 + 32, rem - 32);
+                            load(rc, c0 + 64, rem - 64);
+                            ptx::tmem_ld_wait(ra);
+                            reduce(ra, rem);
+                            if (rem > 32) { ptx::tmem_ld_wait(rb); reduce(rb, rem - 32); }
+                            if (rem > 64) { ptx::tmem_ld_wait(rc); reduce(rc, rem - 64); }
+                        }
+                        m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+                        const long long tq1 = clock64();
+                        st_tmem += tq1 - tq0;
+                        if (last_of_cand) {
+                            const float s = warp_sum(row_ok ? m : 0.f);
+                            if (lane == 0) atomicAdd(&M.out[(size_t)q * M.n_cand + c], s);
+                            m = -std::numeric_limits<float>::infinity();
+                        }
+                        st_sum += clock64() - tq1;
+                    },
+                    [&](int) {
                         ptx::tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) ptx::mbar_arrive(&tempty_bar[tb]);
-                    }
-                    if (warp_ok) {
-                        const float s = warp_sum(row_ok ? m : 0.f);
-                        if (lane == 0) atomicAdd(&M.out[(size_t)q * M.n_cand + c0 + l], s);
-                    }
+                        if (lane == 0) ptx::mbar_arrive(&tempty_bar[g % kMsTBufs]);
+                        ++g;
+                    },
+                    [&](int c) {
+                        // every (padded) doc token is masked to -9999: max = -9999 for each of the lq query tokens
+                        if (team == 0 && ew == 0 && lane == 0) atomicAdd(&M.out[(size_t)q * M.n_cand + c], -9999.f * (float)M.lq);
+                    });
+            }
+            if (M.stats && ew == 0 && lane == 0) {
+                if (team == 0) {
+                    M.stats[blockIdx.x * 8 + 4] = (unsigned long long)st_wait_tfull;
+                    M.stats[blockIdx.x * 8 + 5] = (unsigned long long)(clock64() - st_begin);
+                    M.stats[blockIdx.x * 8 + 6] = (unsigned long long)st_tmem;
+                    M.stats[blockIdx.x * 8 + 7] = (unsigned long long)st_sum;
                 }
             }
         }
@@ -261,19 +346,56 @@ __global__ void __launch_bounds__(kMsThreads, 1) maxsim_kernel(const __grid_cons
 
 using namespace fz;
 
+namespace fz { void* g_debug_stats = nullptr; }
+// debugging aid: device buffer of [n_ctas, 8] uint64 cycle counters filled by the persistent tensor-core kernels
+extern "C" int fz_debug_set_stats(void* device_buffer) {
+    fz::g_debug_stats = device_buffer;
+    return FZ_OK;
+}
+
+extern "C" size_t fz_maxsim_workspace_bytes(int n_queries, int n_cand) {
+    return (size_t)n_queries * (size_t)n_cand * sizeof(int2);
+}
+
 extern "C" int fz_maxsim_bf16(const void* q_tok, int lq, const int32_t* cand_ids, const int64_t* tok_ptr,
                               const void* tok_emb, int64_t n_tokens, int64_t n_docs, int64_t doc_base, int n_queries,
-                              int n_cand, float* out_scores, fz_stream_t stream_) {
+                              int n_cand, float* out_scores, void* ws, size_t ws_bytes, fz_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     FZ_REQUIRE(q_tok && cand_ids && tok_ptr && tok_emb && out_scores, "null pointer");
+    FZ_REQUIRE(ws && ws_bytes >= fz_maxsim_workspace_bytes(n_queries, n_cand) && ((uintptr_t)ws & 7) == 0, "workspace too small");
     FZ_REQUIRE(lq >= 1 && lq <= kMsRows, "lq=%d must be in [1,%d]", lq, kMsRows);
     FZ_REQUIRE(n_tokens >= 1 && n_tokens < (1ll << 31), "n_tokens out of range");
     FZ_REQUIRE(n_docs >= 1 && n_cand >= 1, "bad sizes");
     if (n_queries == 0) return FZ_OK;
     FZ_REQUIRE((long long)n_queries * lq < (1ll << 31), "too many query tokens");
 
+    {
+        const long long n_pairs = (long long)n_queries * n_cand;
+        const int blocks = (int)(ceil_div<long long>(n_pairs, 256) < 148 * 16 ? ceil_div<long long>(n_pairs, 256) : 148 * 16);
+        ProfScope prof("maxsim_info", stream);
+        maxsim_info_kernel<<<blocks, 256, 0, stream>>>(cand_ids, tok_ptr, n_docs, doc_base, n_pairs, (int2*)ws);
+        FZ_LAUNCH_CHECK();
+    }
+    MsArgs M;
+    M.info = (const int2*)ws;
+    M.n_queries = n_queries;
+    M.n_cand = n_cand;
+    M.lq = lq;
+    M.a_rows = (lq + 7) & ~7;
+    M.out = out_scores;
+    M.stats = (unsigned long long*)g_debug_stats;
+    // shared memory: 2 query buffers + kMsStages doc groups + barriers; the UMMA reads 128 query rows per half, so the
+    // 64 KB it may touch past a short query buffer must still be inside the allocation (the stages follow it)
+    const size_t a_bytes = ((size_t)2 * M.a_rows * 128 + 1023) & ~(size_t)1023;
+    const size_t fixed = 1024 /*align*/ + 2 * a_bytes + 256 /*barriers*/;
+    int group_rows = (int)((kMsSmemMax - fixed) / kMsStages / 256) & ~15;
+    if (group_rows > kMsGroupMax) group_rows = kMsGroupMax;
+    M.group_rows = group_rows;
+    const size_t smem = fixed + (size_t)kMsStages * group_rows * 256;
+    FZ_REQUIRE(group_rows >= 64 && smem <= kMsSmemMax, "shared memory plan failed (lq=%d)", lq);
+
     MsMaps maps;
-    int rc = make_bf16_tile_map(&maps.q, q_tok, (uint64_t)n_queries * lq, kMsDim, kMsRows);
+    int rc = make_bf16_tile_map(&maps.q, q_tok, (uint64_t)n_queries * lq, kMsDim, (uint32_t)M.a_rows);
     if (rc) return rc;
     for (int i = 0; i < kMsBoxes; ++i) {
         rc = make_bf16_tile_map(&maps.d[i], tok_emb, (uint64_t)n_tokens, kMsDim, 16 * (i + 1));
@@ -281,26 +403,13 @@ extern "C" int fz_maxsim_bf16(const void* q_tok, int lq, const int32_t* cand_ids
     }
     static bool attr = false;
     if (!attr) {
-        FZ_CUDA(cudaFuncSetAttribute(maxsim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMsSmem));
+        FZ_CUDA(cudaFuncSetAttribute(maxsim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMsSmemMax));
         attr = true;
     }
     FZ_CUDA(cudaMemsetAsync(out_scores, 0, (size_t)n_queries * n_cand * sizeof(float), stream));
-    MsArgs M;
-    M.cand = cand_ids;
-    M.tok_ptr = tok_ptr;
-    M.n_docs = n_docs;
-    M.doc_base = doc_base;
-    M.n_queries = n_queries;
-    M.n_cand = n_cand;
-    M.lq = lq;
-    {
-        const char* e = getenv("FZ_MAXSIM_DEBUG");
-        M.debug = e ? atoi(e) : 0;
-    }
-    M.out = out_scores;
     const int grid = n_queries < num_sms() ? n_queries : num_sms();
     ProfScope prof("maxsim", stream);
-    maxsim_kernel<<<grid, kMsThreads, kMsSmem, stream>>>(maps, M);
+    maxsim_kernel<<<grid, kMsThreads, smem, stream>>>(maps, M);
     FZ_LAUNCH_CHECK();
     return FZ_OK;
 }

@@ -16,8 +16,6 @@
 
 namespace fz {
 
-constexpr int kSparseThreads = 128;      // small CTAs: the per-term barrier only couples 4 warps, 16 CTAs per SM hide latency
-constexpr int kMaxTermsPerPass = 64;
 
 // ------------------------------------------------------------------------------------ index-time helpers
 __global__ void lexical_impacts_kernel(const int64_t* __restrict__ term_ptr, const int32_t* __restrict__ post_doc,
@@ -48,25 +46,6 @@ __global__ void lexical_impacts_kernel(const int64_t* __restrict__ term_ptr, con
     }
 }
 
-__global__ void long_tile_offsets_kernel(const int64_t* __restrict__ term_ptr, const int32_t* __restrict__ post_doc,
-                                         const int32_t* __restrict__ long_terms, int n_long, int tile_docs,
-                                         int n_tiles, uint32_t* __restrict__ out) {
-    const long long total = (long long)n_long * (n_tiles + 1);
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        const int r = (int)(i / (n_tiles + 1)), t = (int)(i % (n_tiles + 1));
-        const int term = long_terms[r];
-        const long long base = term_ptr[term], end = term_ptr[term + 1];
-        const long long first_doc = (long long)t * tile_docs;
-        long long lo = base, hi = end;   // first posting with doc >= first_doc
-        while (lo < hi) {
-            long long mid = (lo + hi) >> 1;
-            if ((long long)post_doc[mid] < first_doc) lo = mid + 1; else hi = mid;
-        }
-        out[i] = (uint32_t)(lo - base);
-    }
-}
-
 // ------------------------------------------------------------------------------------ tile scoring
 template <typename AccT>
 struct SparseArgs {
@@ -75,8 +54,9 @@ struct SparseArgs {
     const int32_t* q_term;
     const float* q_weight;    // f32 only
     int n_queries;
-    int tile_lo;              // first tile of this launch
-    long long r_lo, r_hi;     // doc range of this round
+    int tile_lo, tile_hi;     // tiles of this launch
+    int group_lo;             // first tile group of this launch
+    long long r_lo, r_hi;     // doc range of this round: the whole tile is accumulated, only this range is emitted
     int sign_mode;            // +1: emit score > 0, -1: emit score < 0
     CandState<AccT> st;
     AccT* out_full;           // full mode: [n_queries, n_docs]
@@ -87,129 +67,295 @@ struct SparseArgs {
     int32_t* out_ids;
 };
 
-template <typename AccT> struct ValOf;
-template <> struct ValOf<double> { using type = double; };
-template <> struct ValOf<float> { using type = float; };
+constexpr int kChunks = 4;      // a thread owns one 16-byte vector of docs (4 fp32 / 2 fp64 sums) in each of 4 chunks
+constexpr int kMaxTerms = 128;  // query terms a CTA can hold (longer queries are rejected)
+constexpr int kGroupTiles = FZ_COARSE_TILES;    // consecutive doc tiles one CTA walks for its query
+constexpr int kMaxSparseThreads = 512;
+template <typename AccT> struct AccTraits { static constexpr int kVec = 16 / (int)sizeof(AccT); };
 
-// Accumulate one query's postings that fall into docs [d_lo, d_hi) into acc[0 .. d_hi-d_lo) (shared memory).
-// Terms are applied one after the other: the barrier between terms keeps every doc's sum in query order and makes
-// atomics unnecessary (one term never hits a doc twice).  (A register-prefetch of the next term's first chunk was
-// measured slower: the kernel is bound by L2 traffic and issue slots, not by exposed latency.)
+enum { kKindNone = -1, kKindShort = 0, kKindTiled = 1, kKindDense = 2 };
+
+// The query's terms, resolved ONCE per CTA (term id -> storage form, base, weight; short lists: the few postings that
+// fall into the CTA's tile group, found through the coarse marks).  Under load a dependent global load costs thousands
+// of cycles, so nothing of this chain (q_ptr -> q_term -> term_slot -> base) is repeated per tile.
+struct TermStatic {
+    long long base[kMaxTerms];   // tiled: first posting of the term; dense: row * stride; short: first posting of the group's slice
+    int aux[kMaxTerms];          // tiled: row of the tile-offset table; short: postings in the group's slice
+    int kind[kMaxTerms];
+    float w[kMaxTerms];
+    int n;
+};
+// The terms with at least one posting in the current tile, dense ones first for fp32 (query order for fp64).
+struct TermList {
+    long long lo[kMaxTerms];
+    int len[kMaxTerms];
+    int kind[kMaxTerms];
+    float w[kMaxTerms];
+    unsigned ballot[kMaxTerms / 32][2];      // [warp][0 = active dense, 1 = active scatter]
+    int n;
+};
+
+__device__ __forceinline__ float acc_add(float a, float v, float w) { return __fmaf_rn(v, w, a); }
+__device__ __forceinline__ double acc_add(double a, double v, float) { return __dadd_rn(a, v); }
+
 template <typename AccT>
-__device__ __forceinline__ void accumulate_tile(const SparseArgs<AccT>& A, int q, int tile, long long d_lo,
-                                                long long d_hi, AccT* acc, long long* t_lo, long long* t_hi,
-                                                float* t_w) {
-    using ValT = typename ValOf<AccT>::type;
-    const ValT* __restrict__ vals = reinterpret_cast<const ValT*>(A.ix.post_val);
-    const int32_t* __restrict__ docs = A.ix.post_doc;
-    const int n = (int)(d_hi - d_lo);
-    const int dl = (int)d_lo;
-    {   // zero the tile's accumulators with 16-byte stores (the buffer is 16-byte aligned and padded)
-        int4* z = reinterpret_cast<int4*>(acc);
-        const int n16 = (n * (int)sizeof(AccT) + 15) / 16;
-        for (int i = threadIdx.x; i < n16; i += blockDim.x) z[i] = make_int4(0, 0, 0, 0);
+__device__ __forceinline__ void resolve_terms(const SparseArgs<AccT>& A, int q, int group, TermStatic& S) {
+    const int t = threadIdx.x;
+    const int qb = A.q_ptr[q];
+    const int nt = min(A.q_ptr[q + 1] - qb, kMaxTerms);
+    if (t < kMaxTerms) {
+        int kind = kKindNone, aux = 0;
+        long long base = 0;
+        float w = 1.0f;
+        if (t < nt) {
+            const int term = A.q_term[qb + t];
+            if (A.q_weight) w = A.q_weight[qb + t];
+            if (term >= 0 && term < A.ix.n_terms) {
+                const int slot = A.ix.term_slot[term];
+                if (slot >= 0) {
+                    kind = kKindTiled;
+                    base = A.ix.tiled_base[slot];
+                    aux = slot;
+                } else if (slot <= -2) {
+                    kind = kKindDense;
+                    base = (long long)(-2 - slot) * A.ix.dense_stride;
+                } else {
+                    const long long b0 = A.ix.term_ptr[term];
+                    if (A.ix.term_ptr[term + 1] > b0) {
+                        const uint16_t* cm = A.ix.short_coarse + (size_t)term * (A.ix.n_coarse + 1) + group;
+                        const int c0 = cm[0], c1 = cm[1];
+                        if (c1 > c0) {
+                            kind = kKindShort;
+                            base = b0 + c0;
+                            aux = c1 - c0;
+                        }
+                    }
+                }
+            }
+        }
+        S.base[t] = base;
+        S.aux[t] = aux;
+        S.kind[t] = kind;
+        S.w[t] = w;
     }
-    const int qb = A.q_ptr[q], qe = A.q_ptr[q + 1];
-    for (int pass = qb; pass < qe; pass += kMaxTermsPerPass) {
-        const int nt = min(kMaxTermsPerPass, qe - pass);
-        __syncthreads();
-        // resolve every term's posting range for this tile in parallel (one latency chain, not one per term)
-        if ((int)threadIdx.x < nt) {
-            const int t = A.q_term[pass + threadIdx.x];
-            long long lo = 0, hi = 0;
-            if (t >= 0 && t < A.ix.n_terms) {
-                const long long base = A.ix.term_ptr[t];
-                const int lr = A.ix.long_row[t];
-                if (lr >= 0) {
-                    const uint32_t* o = A.ix.long_tile_off + (size_t)lr * (A.ix.n_tiles + 1) + tile;
-                    lo = base + o[0];
-                    hi = base + o[1];
-                } else {
-                    lo = base;
-                    hi = A.ix.term_ptr[t + 1];
+    if (t == 0) S.n = nt;
+}
+
+// Accumulate one query's postings that fall into tile `tile` (docs [d_lo, d_lo + tile_docs)) into acc[0 .. tile_docs).
+//
+// A thread owns one 16-byte vector of docs in every chunk of kVec * blockDim docs.  Dense terms are added to those docs'
+// running sums in REGISTERS with coalesced 16-byte loads; tiled and short terms scatter into shared memory, one term
+// after the other: the barrier between terms keeps every doc's sum in query order (fp64 lexical scores are summed left
+// to right like src/retrievers/bm25.py:152-155) and makes atomics unnecessary (one term never hits a doc twice).  The
+// running sums move between registers and shared memory whenever the storage form of the next term changes, so the
+// order of the additions is exactly the query order for fp64; fp32 (SPLADE, order-free within the stated tolerance)
+// takes all dense terms first.  Terms with no posting in the tile are dropped when the tile's term list is built.
+// (o0, o1) are this thread's term's segment bounds in the tile (tiled terms), loaded one tile ahead by the caller.
+// acc needs kVec * kChunks * blockDim + 4 slots; slot tile_docs is the dump slot of the padding postings.
+template <typename AccT>
+__device__ __forceinline__ void accumulate_tile(const SparseArgs<AccT>& A, int tile, long long d_lo, AccT* acc,
+                                                const TermStatic& S, TermList& L, uint32_t o0, uint32_t o1) {
+    constexpr int kVec = AccTraits<AccT>::kVec;
+    constexpr bool kF64 = std::is_same<AccT, double>::value;
+    using Vec = typename std::conditional<kF64, double2, float4>::type;
+    using OffVec = typename std::conditional<kF64, uint32_t, uint2>::type;      // kVec uint16 offsets
+    const AccT* __restrict__ short_val = reinterpret_cast<const AccT*>(A.ix.post_val);
+    const AccT* __restrict__ tiled_val = reinterpret_cast<const AccT*>(A.ix.tiled_val);
+    const AccT* __restrict__ dense_val = reinterpret_cast<const AccT*>(A.ix.dense_val);
+    const int T = blockDim.x, t = threadIdx.x;
+    const int tile_docs = A.ix.tile_docs;
+    const int dl = (int)d_lo;
+
+    // ---- the tile's term list (threads 0 .. kMaxTerms-1 hold one term each; every CTA has at least that many)
+    long long lo = 0;
+    int len = 0, kind = kKindNone;
+    unsigned bd = 0, bs = 0;
+    if (t < kMaxTerms) {
+        kind = S.kind[t];
+        if (kind == kKindTiled) {
+            lo = S.base[t] + o0;
+            len = (int)(o1 - o0);
+        } else if (kind == kKindDense) {
+            lo = S.base[t] + (long long)tile * tile_docs;
+            len = tile_docs;
+        } else if (kind == kKindShort) {
+            lo = S.base[t];
+            len = S.aux[t];         // the group's slice: the scatter checks the tile bounds
+        }
+        bd = __ballot_sync(0xffffffffu, len > 0 && kind == kKindDense);
+        bs = __ballot_sync(0xffffffffu, len > 0 && kind != kKindDense);
+        if ((t & 31) == 0) { L.ballot[t >> 5][0] = bd; L.ballot[t >> 5][1] = bs; }
+    }
+    __syncthreads();
+    if (t < kMaxTerms) {
+        const int wi = t >> 5;
+        const unsigned below = (1u << (t & 31)) - 1;
+        int dense_before = __popc(bd & below), scat_before = __popc(bs & below), n_dense = 0, n_scat = 0;
+#pragma unroll
+        for (int w2 = 0; w2 < kMaxTerms / 32; ++w2) {
+            const int nd = __popc(L.ballot[w2][0]), ns = __popc(L.ballot[w2][1]);
+            if (w2 < wi) { dense_before += nd; scat_before += ns; }
+            n_dense += nd;
+            n_scat += ns;
+        }
+        if (len > 0) {
+            int pos;
+            if (kF64) pos = dense_before + scat_before;                       // query order
+            else pos = kind == kKindDense ? dense_before : n_dense + scat_before;
+            L.lo[pos] = lo;
+            L.len[pos] = len;
+            L.kind[pos] = kind;
+            L.w[pos] = S.w[t];
+        }
+        if (t == 0) L.n = n_dense + n_scat;
+    }
+    __syncthreads();
+
+    Vec racc[kChunks];
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) {
+        if constexpr (kF64) racc[c] = make_double2(0.0, 0.0); else racc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    bool in_reg = true;       // the running sums of this thread's docs live in racc (shared memory is stale)
+
+    // (Issuing the next scatter term's global loads before the current term's read-modify-write, and pairing dense rows,
+    // were both measured slower: the extra registers cost more occupancy than the shorter dependency chain wins.)
+    const int n_active = L.n;
+    for (int j = 0; j < n_active; ++j) {
+        const int jlen = L.len[j];
+        const int jkind = L.kind[j];
+        const float jw = L.w[j];
+        const long long jlo = L.lo[j];
+        if (jkind == kKindDense) {
+            if (!in_reg) {      // the last scatter ended with a barrier
+#pragma unroll
+                for (int c = 0; c < kChunks; ++c) racc[c] = *reinterpret_cast<const Vec*>(acc + (size_t)(c * T + t) * kVec);
+                in_reg = true;
+            }
+            const AccT* __restrict__ src = dense_val + jlo;
+#pragma unroll
+            for (int c = 0; c < kChunks; ++c) {
+                const int i = (c * T + t) * kVec;
+                if (i < tile_docs) {
+                    const Vec a = __ldg(reinterpret_cast<const Vec*>(src + i));
+                    if constexpr (kF64) {
+                        racc[c].x = __dadd_rn(racc[c].x, a.x); racc[c].y = __dadd_rn(racc[c].y, a.y);
+                    } else {
+                        racc[c].x = __fmaf_rn(a.x, jw, racc[c].x); racc[c].y = __fmaf_rn(a.y, jw, racc[c].y);
+                        racc[c].z = __fmaf_rn(a.z, jw, racc[c].z); racc[c].w = __fmaf_rn(a.w, jw, racc[c].w);
+                    }
                 }
             }
-            t_lo[threadIdx.x] = lo;
-            t_hi[threadIdx.x] = hi;
-            t_w[threadIdx.x] = A.q_weight ? A.q_weight[pass + threadIdx.x] : 1.0f;
+            continue;
         }
-        __syncthreads();
-        for (int j = 0; j < nt; ++j) {
-            const int32_t* __restrict__ dj = docs + t_lo[j];
-            const ValT* __restrict__ vj = vals + t_lo[j];
-            const int len = (int)(t_hi[j] - t_lo[j]);
-            const float w = t_w[j];
-            // two postings per thread and iteration, doc and value loads issued together (no load behind a branch)
-            for (int p = threadIdx.x; p < len; p += 2 * blockDim.x) {
-                const int p1 = p + blockDim.x;
-                const bool ok1 = p1 < len;
-                const int d0 = __ldg(dj + p);
-                const ValT v0 = __ldg(vj + p);
-                const int d1 = ok1 ? __ldg(dj + p1) : dl - 1;
-                const ValT v1 = ok1 ? __ldg(vj + p1) : (ValT)0;
-                const unsigned o0 = (unsigned)(d0 - dl), o1 = (unsigned)(d1 - dl);   // one unsigned compare covers both bounds
-                if constexpr (std::is_same<AccT, double>::value) {
-                    if (o0 < (unsigned)n) acc[o0] = __dadd_rn(acc[o0], v0);
-                    if (o1 < (unsigned)n) acc[o1] = __dadd_rn(acc[o1], v1);
+        if (in_reg) {
+#pragma unroll
+            for (int c = 0; c < kChunks; ++c) *reinterpret_cast<Vec*>(acc + (size_t)(c * T + t) * kVec) = racc[c];
+            __syncthreads();
+            in_reg = false;
+        }
+        if (jkind == kKindTiled) {
+            // kVec postings per thread and step: one load of uint16 offsets, one 16-byte load of values
+            const uint16_t* __restrict__ op = A.ix.tiled_off + jlo;
+            const AccT* __restrict__ vp = tiled_val + jlo;
+            for (int i = kVec * t; i < jlen; i += kVec * T) {
+                const OffVec o = __ldg(reinterpret_cast<const OffVec*>(op + i));
+                const Vec v = __ldg(reinterpret_cast<const Vec*>(vp + i));
+                if constexpr (kF64) {
+                    const unsigned i0 = o & 0xffffu, i1 = o >> 16;
+                    acc[i0] = __dadd_rn(acc[i0], v.x);
+                    acc[i1] = __dadd_rn(acc[i1], v.y);
                 } else {
-                    if (o0 < (unsigned)n) acc[o0] = __fmaf_rn(v0, w, acc[o0]);
-                    if (o1 < (unsigned)n) acc[o1] = __fmaf_rn(v1, w, acc[o1]);
+                    const unsigned i0 = o.x & 0xffffu, i1 = o.x >> 16, i2 = o.y & 0xffffu, i3 = o.y >> 16;
+                    acc[i0] = __fmaf_rn(v.x, jw, acc[i0]);
+                    acc[i1] = __fmaf_rn(v.y, jw, acc[i1]);
+                    acc[i2] = __fmaf_rn(v.z, jw, acc[i2]);
+                    acc[i3] = __fmaf_rn(v.w, jw, acc[i3]);
                 }
             }
-            __syncthreads();   // the next term may hit the same docs
+        } else {
+            const int32_t* __restrict__ dj = A.ix.post_doc + jlo;
+            const AccT* __restrict__ vj = short_val + jlo;
+            for (int p = t; p < jlen; p += T) {
+                const unsigned o = (unsigned)(__ldg(dj + p) - dl);
+                if (o < (unsigned)tile_docs) acc[o] = acc_add(acc[o], __ldg(vj + p), jw);
+            }
         }
+        __syncthreads();   // the next term may hit the same docs
+    }
+    if (in_reg) {
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) *reinterpret_cast<Vec*>(acc + (size_t)(c * T + t) * kVec) = racc[c];
     }
     __syncthreads();
 }
 
+// segment bounds of this thread's term in `tile` (tiled terms only)
+template <typename AccT>
+__device__ __forceinline__ uint32_t tile_offset(const SparseArgs<AccT>& A, const TermStatic& S, int tile) {
+    const int t = threadIdx.x;
+    if (t < kMaxTerms && S.kind[t] == kKindTiled)
+        return __ldg(A.ix.tiled_tile_off + (size_t)S.aux[t] * (A.ix.n_tiles + 1) + tile);
+    return 0;
+}
+
+// One CTA = one query x one group of kGroupTiles consecutive doc tiles (CTAs are ordered group-major, so all queries
+// stream the same slice of the posting lists at the same time and the slice is served from L2 / L1).
 template <typename AccT, int MODE>   // MODE 0: threshold emit, 1: store every score
-__global__ void __launch_bounds__(kSparseThreads) sparse_tile_kernel(const SparseArgs<AccT> A) {
+__global__ void __launch_bounds__(kMaxSparseThreads) sparse_tile_kernel(const SparseArgs<AccT> A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     AccT* acc = reinterpret_cast<AccT*>(smem_raw);
-    __shared__ long long t_lo[kMaxTermsPerPass], t_hi[kMaxTermsPerPass];
-    __shared__ float t_w[kMaxTermsPerPass];
+    __shared__ TermStatic S;
+    __shared__ TermList L;
 
-    const int tile = A.tile_lo + blockIdx.x / A.n_queries;
+    const int group = A.group_lo + blockIdx.x / A.n_queries;
     const int q = blockIdx.x % A.n_queries;
-    long long d_lo = (long long)tile * A.ix.tile_docs;
-    long long d_hi = min(d_lo + A.ix.tile_docs, (long long)A.ix.n_docs);
-    if (MODE == 0) {
-        d_lo = max(d_lo, A.r_lo);
-        d_hi = min(d_hi, A.r_hi);
-    }
-    if (d_hi <= d_lo) return;
-    accumulate_tile<AccT>(A, q, tile, d_lo, d_hi, acc, t_lo, t_hi, t_w);
-    const int n = (int)(d_hi - d_lo);
-    if (MODE == 1) {
-        AccT* out = A.out_full + (size_t)q * A.ix.n_docs + d_lo;
-        for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = acc[i];
-        return;
-    }
-    const AccT tau = A.st.tau[q];
-    // scan the tile 16 bytes at a time; survivors are rare once tau has risen, so the common case is one compare
-    constexpr int V = 16 / (int)sizeof(AccT);
-    const AccT lim = A.sign_mode > 0 ? (tau > (AccT)0 ? tau : (AccT)0) : tau;
-    for (int i0 = threadIdx.x * V; i0 < n; i0 += blockDim.x * V) {
-        AccT v[V];
-        *reinterpret_cast<int4*>(v) = *reinterpret_cast<const int4*>(acc + i0);
+    const int t_begin = max(group * kGroupTiles, A.tile_lo), t_end = min((group + 1) * kGroupTiles, A.tile_hi);
+    resolve_terms<AccT>(A, q, group, S);
+    const AccT tau = MODE == 0 ? A.st.tau[q] : (AccT)0;
+    __syncthreads();
+    uint32_t o0 = tile_offset<AccT>(A, S, t_begin), o1 = tile_offset<AccT>(A, S, t_begin + 1);
+    for (int tile = t_begin; tile < t_end; ++tile) {
+        const uint32_t o2 = tile + 1 < t_end ? tile_offset<AccT>(A, S, tile + 2) : 0;      // next tile's bound, in flight
+        const long long d_lo = (long long)tile * A.ix.tile_docs;
+        const long long d_hi = min(d_lo + A.ix.tile_docs, (long long)A.ix.n_docs);
+        accumulate_tile<AccT>(A, tile, d_lo, acc, S, L, o0, o1);
+        o0 = o1;
+        o1 = o2;
+        if (MODE == 1) {
+            const int n = (int)(d_hi - d_lo);
+            AccT* out = A.out_full + (size_t)q * A.ix.n_docs + d_lo;
+            for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = acc[i];
+        } else {
+            // emit only the docs of this round; a tile that straddles a round boundary is accumulated by both rounds
+            const int e_lo = (int)(max(d_lo, A.r_lo) - d_lo), e_hi = (int)(min(d_hi, A.r_hi) - d_lo);
+            // scan the tile 16 bytes at a time; survivors are rare once tau has risen: the common case is one compare
+            constexpr int V = 16 / (int)sizeof(AccT);
+            const AccT lim = A.sign_mode > 0 ? (tau > (AccT)0 ? tau : (AccT)0) : tau;
+            for (int i0 = (e_lo / V) * V + threadIdx.x * V; i0 < e_hi; i0 += blockDim.x * V) {
+                AccT v[V];
+                *reinterpret_cast<int4*>(v) = *reinterpret_cast<const int4*>(acc + i0);
 #pragma unroll
-        for (int u = 0; u < V; ++u) {
-            const AccT sc = v[u];
-            const bool want = A.sign_mode > 0 ? (sc > lim) : (sc < (AccT)0 && sc > lim);
-            if (want && i0 + u < n) cand_append<AccT>(A.st, q, sc, (int32_t)(d_lo + i0 + u));
+                for (int u = 0; u < V; ++u) {
+                    const AccT sc = v[u];
+                    const bool want = A.sign_mode > 0 ? (sc > lim) : (sc < (AccT)0 && sc > lim);
+                    if (want && i0 + u >= e_lo && i0 + u < e_hi) cand_append<AccT>(A.st, q, sc, (int32_t)(d_lo + i0 + u));
+                }
+            }
         }
+        // the next tile's term list is written only after its first barrier, which every thread reaches after this scan
     }
 }
 
 // Queries with fewer than k positive-score docs: append zero-score docs in ascending doc-id order
 // (the reference ranks every document; unmatched ones score exactly 0.0 and tie by index, bm25.py:103-105).
 template <typename AccT>
-__global__ void __launch_bounds__(kSparseThreads) sparse_zero_fill_kernel(const SparseArgs<AccT> A) {
+__global__ void __launch_bounds__(kMaxSparseThreads) sparse_zero_fill_kernel(const SparseArgs<AccT> A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     AccT* acc = reinterpret_cast<AccT*>(smem_raw);
-    __shared__ long long t_lo[kMaxTermsPerPass], t_hi[kMaxTermsPerPass];
-    __shared__ float t_w[kMaxTermsPerPass];
-    __shared__ int s_warp[kSparseThreads / 32];
+    __shared__ TermStatic S;
+    __shared__ TermList L;
+    __shared__ int s_warp[kMaxSparseThreads / 32];
     __shared__ int s_found;
 
     const int q = blockIdx.x;
@@ -217,15 +363,21 @@ __global__ void __launch_bounds__(kSparseThreads) sparse_zero_fill_kernel(const 
     const int n_have = A.st.cnt[q];
     if (n_have >= A.k || A.sign_mode < 0) return;           // negatives never need zero fill
     const int need = A.k - n_have;
+    const int n_warps = blockDim.x >> 5;
     if (threadIdx.x == 0) {
         s_found = 0;
         A.st.status[q] |= FZ_STATUS_NEED_ZERO;
     }
     __syncthreads();
     for (int tile = 0; tile < A.ix.n_tiles; ++tile) {
+        if (tile % kGroupTiles == 0) {
+            __syncthreads();
+            resolve_terms<AccT>(A, q, tile / kGroupTiles, S);
+            __syncthreads();
+        }
         const long long d_lo = (long long)tile * A.ix.tile_docs;
         const long long d_hi = min(d_lo + A.ix.tile_docs, (long long)A.ix.n_docs);
-        accumulate_tile<AccT>(A, q, tile, d_lo, d_hi, acc, t_lo, t_hi, t_w);
+        accumulate_tile<AccT>(A, tile, d_lo, acc, S, L, tile_offset<AccT>(A, S, tile), tile_offset<AccT>(A, S, tile + 1));
         const int n = (int)(d_hi - d_lo);
         for (int c0 = 0; c0 < n; c0 += blockDim.x) {
             const int i = c0 + threadIdx.x;
@@ -236,7 +388,7 @@ __global__ void __launch_bounds__(kSparseThreads) sparse_zero_fill_kernel(const 
             if (lane == 0) s_warp[warp] = __popc(bal);
             __syncthreads();
             int before = 0, total = 0;
-            for (int w = 0; w < kSparseThreads / 32; ++w) {
+            for (int w = 0; w < n_warps; ++w) {
                 const int v = s_warp[w];
                 if (w < warp) before += v;
                 total += v;
@@ -258,14 +410,31 @@ __global__ void __launch_bounds__(kSparseThreads) sparse_zero_fill_kernel(const 
     if (threadIdx.x == 0 && s_found < need) A.st.status[q] |= FZ_STATUS_NEED_NEG;
 }
 
-static int check_index(const fz_postings_t* ix, size_t acc_bytes) {
-    FZ_REQUIRE(ix && ix->term_ptr && ix->post_doc && ix->post_val && ix->long_row, "null index pointer");
-    FZ_REQUIRE(ix->n_long == 0 || ix->long_tile_off, "long_tile_off missing");
-    FZ_REQUIRE(ix->tile_docs >= 256 && ix->tile_docs % 256 == 0, "tile_docs=%d must be a positive multiple of 256",
-               ix->tile_docs);
-    FZ_REQUIRE((size_t)ix->tile_docs * acc_bytes <= 200 * 1024, "tile_docs=%d does not fit shared memory", ix->tile_docs);
+// threads per CTA: every thread owns 4 docs in each of kChunks chunks
+template <typename AccT>
+static int sparse_threads(int tile_docs) {
+    const int per_thread = AccTraits<AccT>::kVec * kChunks;
+    int t = (tile_docs + per_thread - 1) / per_thread;
+    t = (t + 31) / 32 * 32;
+    return t < kMaxTerms ? kMaxTerms : t;       // kMaxTerms threads resolve the terms
+}
+template <typename AccT>
+static size_t sparse_smem(int tile_docs) {
+    return ((size_t)AccTraits<AccT>::kVec * kChunks * sparse_threads<AccT>(tile_docs) + 4) * sizeof(AccT);
+}
+
+template <typename AccT>
+static int check_index(const fz_postings_t* ix) {
+    FZ_REQUIRE(ix && ix->term_ptr && ix->term_slot && ix->short_coarse, "null index pointer");
+    FZ_REQUIRE(ix->n_coarse == (ix->n_tiles + FZ_COARSE_TILES - 1) / FZ_COARSE_TILES, "n_coarse inconsistent with n_tiles");
+    FZ_REQUIRE(ix->n_tiled == 0 || (ix->tiled_base && ix->tiled_tile_off && ix->tiled_off && ix->tiled_val), "tiled postings missing");
+    FZ_REQUIRE(ix->n_dense == 0 || ix->dense_val, "dense rows missing");
+    FZ_REQUIRE(ix->tile_docs >= 4 && ix->tile_docs % 4 == 0, "tile_docs=%d must be a positive multiple of 4", ix->tile_docs);
+    FZ_REQUIRE(sparse_threads<AccT>(ix->tile_docs) <= kMaxSparseThreads, "tile_docs=%d too large (max %d for this score type)",
+               ix->tile_docs, AccTraits<AccT>::kVec * kChunks * kMaxSparseThreads);
     FZ_REQUIRE(ix->n_docs >= 1 && ix->n_docs < (1ll << 31), "n_docs out of range");
     FZ_REQUIRE(ix->n_tiles == (int)ceil_div<long long>(ix->n_docs, ix->tile_docs), "n_tiles inconsistent with n_docs");
+    FZ_REQUIRE(ix->dense_stride == (long long)ix->n_tiles * ix->tile_docs, "dense_stride must be n_tiles * tile_docs");
     return FZ_OK;
 }
 
@@ -285,7 +454,7 @@ template <typename AccT>
 static int sparse_topk(const fz_postings_t* ix, const int32_t* q_ptr, const int32_t* q_term, const float* q_weight,
                        int n_queries, int k, int64_t doc_base, int cap, int growth, int sign_mode, AccT* out_scores,
                        int32_t* out_ids, int32_t* out_status, void* ws, size_t ws_bytes, cudaStream_t stream) {
-    int rc = check_index(ix, sizeof(AccT));
+    int rc = check_index<AccT>(ix);
     if (rc) return rc;
     FZ_REQUIRE(q_ptr && q_term && out_scores && out_ids && out_status, "null pointer");
     FZ_REQUIRE(k >= 1 && cap >= 2 * k && cap <= 8192, "need 1 <= k, 2k <= cap <= 8192 (k=%d cap=%d)", k, cap);
@@ -312,19 +481,26 @@ static int sparse_topk(const fz_postings_t* ix, const int32_t* q_ptr, const int3
     rc = cand_init<AccT>(A.st, n_queries, stream);
     if (rc) return rc;
 
-    const size_t smem = (size_t)ix->tile_docs * sizeof(AccT);
+    const int threads = sparse_threads<AccT>(ix->tile_docs);
+    const size_t smem = sparse_smem<AccT>(ix->tile_docs);
     const long long N = ix->n_docs;
-    long long lo = 0, hi = N < cap ? N : cap;
+    // Rounds end on tile boundaries where that keeps them overflow-free (a tile cut by a boundary is accumulated twice)
+    auto align_hi = [&](long long lo, long long hi) {
+        const long long a = hi / ix->tile_docs * ix->tile_docs;
+        return a > lo ? a : hi;
+    };
+    long long lo = 0, hi = N < cap ? N : align_hi(0, cap);
     while (true) {
         A.r_lo = lo;
         A.r_hi = hi;
         A.tile_lo = (int)(lo / ix->tile_docs);
-        const int tile_hi = (int)ceil_div<long long>(hi, ix->tile_docs);
-        const long long blocks = (long long)(tile_hi - A.tile_lo) * n_queries;
+        A.tile_hi = (int)ceil_div<long long>(hi, ix->tile_docs);
+        A.group_lo = A.tile_lo / kGroupTiles;
+        const long long blocks = (long long)(ceil_div(A.tile_hi, kGroupTiles) - A.group_lo) * n_queries;
         FZ_REQUIRE(blocks < (1ll << 31), "grid too large");
         {
             ProfScope prof(sizeof(AccT) == 8 ? "sparse_tile_f64" : "sparse_tile_f32", stream);
-            sparse_tile_kernel<AccT, 0><<<(unsigned)blocks, kSparseThreads, smem, stream>>>(A);
+            sparse_tile_kernel<AccT, 0><<<(unsigned)blocks, threads, smem, stream>>>(A);
         }
         FZ_LAUNCH_CHECK();
         const bool last = hi >= N;
@@ -333,10 +509,10 @@ static int sparse_topk(const fz_postings_t* ix, const int32_t* q_ptr, const int3
         if (last) break;
         lo = hi;
         hi = growth >= 2 ? hi * growth : hi + (cap - k);
-        if (hi > N) hi = N;
+        if (hi >= N) hi = N; else hi = align_hi(lo, hi);
     }
     ProfScope prof("sparse_zero_fill", stream);
-    sparse_zero_fill_kernel<AccT><<<n_queries, kSparseThreads, smem, stream>>>(A);
+    sparse_zero_fill_kernel<AccT><<<n_queries, threads, smem, stream>>>(A);
     FZ_LAUNCH_CHECK();
     return FZ_OK;
 }
@@ -344,7 +520,7 @@ static int sparse_topk(const fz_postings_t* ix, const int32_t* q_ptr, const int3
 template <typename AccT>
 static int sparse_scores(const fz_postings_t* ix, const int32_t* q_ptr, const int32_t* q_term, const float* q_weight,
                          int n_queries, AccT* out, cudaStream_t stream) {
-    int rc = check_index(ix, sizeof(AccT));
+    int rc = check_index<AccT>(ix);
     if (rc) return rc;
     FZ_REQUIRE(q_ptr && q_term && out, "null pointer");
     if (n_queries == 0) return FZ_OK;
@@ -358,9 +534,12 @@ static int sparse_scores(const fz_postings_t* ix, const int32_t* q_ptr, const in
     A.q_weight = q_weight;
     A.n_queries = n_queries;
     A.out_full = out;
-    const long long blocks = (long long)ix->n_tiles * n_queries;
+    A.tile_lo = 0;
+    A.tile_hi = ix->n_tiles;
+    A.group_lo = 0;
+    const long long blocks = (long long)ceil_div(ix->n_tiles, kGroupTiles) * n_queries;
     FZ_REQUIRE(blocks < (1ll << 31), "grid too large");
-    sparse_tile_kernel<AccT, 1><<<(unsigned)blocks, kSparseThreads, (size_t)ix->tile_docs * sizeof(AccT), stream>>>(A);
+    sparse_tile_kernel<AccT, 1><<<(unsigned)blocks, sparse_threads<AccT>(ix->tile_docs), sparse_smem<AccT>(ix->tile_docs), stream>>>(A);
     FZ_LAUNCH_CHECK();
     return FZ_OK;
 }
@@ -381,18 +560,6 @@ int fz_lexical_impacts(const int64_t* term_ptr, const int32_t* post_doc, const i
     int blocks = (int)(ceil_div<long long>(nnz, 256) < 148 * 32 ? ceil_div<long long>(nnz, 256) : 148 * 32);
     lexical_impacts_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(term_ptr, post_doc, post_tf, doc_len, idf, n_terms,
                                                                      nnz, avgdl, k1, k1 + 1, 1 - b, b, variant, out_impact);
-    FZ_LAUNCH_CHECK();
-    return FZ_OK;
-}
-
-int fz_long_tile_offsets(const int64_t* term_ptr, const int32_t* post_doc, const int32_t* long_terms, int32_t n_long,
-                         int32_t tile_docs, int32_t n_tiles, uint32_t* out_long_tile_off, fz_stream_t stream) {
-    if (n_long == 0) return FZ_OK;
-    FZ_REQUIRE(term_ptr && post_doc && long_terms && out_long_tile_off, "null pointer");
-    long long total = (long long)n_long * (n_tiles + 1);
-    int blocks = (int)(ceil_div<long long>(total, 256) < 148 * 32 ? ceil_div<long long>(total, 256) : 148 * 32);
-    long_tile_offsets_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(term_ptr, post_doc, long_terms, n_long, tile_docs,
-                                                                       n_tiles, out_long_tile_off);
     FZ_LAUNCH_CHECK();
     return FZ_OK;
 }

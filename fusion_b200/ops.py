@@ -15,6 +15,7 @@ from . import _lib
 from ._lib import FZ_STATUS_NEED_NEG, FZ_STATUS_OVERFLOW, FusionB200Error, check
 
 DEFAULT_CAP = 8192
+COARSE_TILES = 16          # FZ_COARSE_TILES
 DEFAULT_GROWTH = 4
 
 
@@ -142,12 +143,17 @@ def fuse(lists, method: str, normalization: str | None = None, weights=None, dis
 # ----------------------------------------------------------------------------------------------- K2
 @dataclass
 class PostingsView:
-    """Device CSR postings + tile table, as the C struct wants them (see fusion_b200.index)."""
-    term_ptr: torch.Tensor       # int64 [V+1]
-    post_doc: torch.Tensor       # int32 [nnz]
-    post_val: torch.Tensor       # float64 | float32 [nnz]
-    long_row: torch.Tensor       # int32 [V]
-    long_tile_off: torch.Tensor  # uint32 viewed as int32 [n_long, n_tiles+1]
+    """Device postings in the three storage forms of ``fz_postings_t`` (built by fusion_b200.index.build_postings)."""
+    term_ptr: torch.Tensor        # int64 [V+1]   short lists
+    post_doc: torch.Tensor        # int32
+    post_val: torch.Tensor        # float64 | float32
+    short_coarse: torch.Tensor    # uint16 payload in int16 [V, n_coarse+1]
+    term_slot: torch.Tensor       # int32 [V]
+    tiled_base: torch.Tensor      # int64 [n_tiled]
+    tiled_tile_off: torch.Tensor  # uint32 payload in int32 [n_tiled, n_tiles+1]
+    tiled_off: torch.Tensor       # uint16 payload in int16
+    tiled_val: torch.Tensor
+    dense_val: torch.Tensor       # [n_dense, n_tiles*tile_docs]
     n_docs: int
     tile_docs: int
 
@@ -155,19 +161,42 @@ class PostingsView:
     def n_tiles(self) -> int:
         return (self.n_docs + self.tile_docs - 1) // self.tile_docs
 
+    @property
+    def dtype(self) -> torch.dtype:
+        return self.post_val.dtype
+
+    def tensors(self):
+        return (self.term_ptr, self.post_doc, self.post_val, self.short_coarse, self.term_slot, self.tiled_base, self.tiled_tile_off,
+                self.tiled_off, self.tiled_val, self.dense_val)
+
+    def nbytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in self.tensors())
+
     def c_struct(self) -> _lib.Postings:
-        return _lib.Postings(self.term_ptr.data_ptr(), self.post_doc.data_ptr(), self.post_val.data_ptr(),
-                             self.long_row.data_ptr(), self.long_tile_off.data_ptr() if self.long_tile_off.numel() else 0,
-                             self.term_ptr.numel() - 1, self.long_tile_off.shape[0], self.n_docs, self.tile_docs,
-                             self.n_tiles)
+        p = lambda t: t.data_ptr() if t.numel() else 0
+        return _lib.Postings(self.term_ptr.data_ptr(), p(self.post_doc), p(self.post_val), p(self.short_coarse),
+                             self.term_slot.data_ptr(),
+                             p(self.tiled_base), p(self.tiled_tile_off), p(self.tiled_off), p(self.tiled_val),
+                             p(self.dense_val), self.n_tiles * self.tile_docs, self.term_ptr.numel() - 1,
+                             self.tiled_base.numel(), self.dense_val.shape[0], self.tile_docs, self.n_tiles,
+                             (self.n_tiles + COARSE_TILES - 1) // COARSE_TILES, self.n_docs)
+
+
+MAX_QUERY_TERMS = 128     # kMaxTerms in csrc/sparse.cu: the terms of a query are held once per CTA
+
+
+def _check_query_lengths(q_ptr: torch.Tensor) -> None:
+    if q_ptr.numel() > 1 and int((q_ptr[1:] - q_ptr[:-1]).max()) > MAX_QUERY_TERMS:
+        raise FusionB200Error(f"a query has more than {MAX_QUERY_TERMS} terms (tokens, duplicates counted); "
+                              "the inverted-index kernels hold a query's terms in shared memory")
 
 
 def _sparse_topk_once(pv: PostingsView, q_ptr, q_term, q_weight, k, doc_base, cap, growth, sign_mode):
     lib = _lib.load()
-    f64 = pv.post_val.dtype == torch.float64
-    dev = pv.post_doc.device
+    f64 = pv.dtype == torch.float64
+    dev = pv.term_ptr.device
     nq = q_ptr.numel() - 1
-    out_s = torch.empty((nq, k), dtype=pv.post_val.dtype, device=dev)
+    out_s = torch.empty((nq, k), dtype=pv.dtype, device=dev)
     out_i = torch.empty((nq, k), dtype=torch.int32, device=dev)
     status = torch.empty((nq,), dtype=torch.int32, device=dev)
     ws = _ws(lib.fz_sparse_topk_workspace_bytes(nq, k, cap, 1 if f64 else 0), dev)
@@ -207,6 +236,7 @@ def sparse_topk(pv: PostingsView, q_ptr, q_term, q_weight, k: int, doc_base: int
     q_term = _req(q_term, torch.int32, "q_term")
     if q_weight is not None:
         q_weight = _req(q_weight, torch.float32, "q_weight")
+    _check_query_lengths(q_ptr)
     k_eff = min(k, pv.n_docs)
     cap = max(cap, 2 * k_eff)
     out_s, out_i, status = _sparse_topk_once(pv, q_ptr, q_term, q_weight, k_eff, doc_base, cap, growth, +1)
@@ -239,9 +269,10 @@ def sparse_scores(pv: PostingsView, q_ptr, q_term, q_weight=None):
     lib = _lib.load()
     q_ptr = _req(q_ptr, torch.int32, "q_ptr")
     q_term = _req(q_term, torch.int32, "q_term")
+    _check_query_lengths(q_ptr)
     nq = q_ptr.numel() - 1
-    f64 = pv.post_val.dtype == torch.float64
-    out = torch.empty((nq, pv.n_docs), dtype=pv.post_val.dtype, device=pv.post_doc.device)
+    f64 = pv.dtype == torch.float64
+    out = torch.empty((nq, pv.n_docs), dtype=pv.dtype, device=pv.term_ptr.device)
     st = pv.c_struct()
     if f64:
         check(lib.fz_sparse_scores_f64(C.byref(st), _ptr(q_ptr), _ptr(q_term), nq, _ptr(out), _stream(out)),
@@ -262,16 +293,6 @@ def lexical_impacts(term_ptr, post_doc, post_tf, doc_len, idf, avgdl: float, k1:
                                  _ptr(None if doc_len is None else _req(doc_len, torch.int32, "doc_len")),
                                  _ptr(_req(idf, torch.float64, "idf")), term_ptr.numel() - 1, post_doc.numel(),
                                  float(avgdl), float(k1), float(b), variant, _ptr(out), _stream(out)), "fz_lexical_impacts")
-    return out
-
-
-def long_tile_offsets(term_ptr, post_doc, long_terms, tile_docs: int, n_tiles: int):
-    lib = _lib.load()
-    n_long = long_terms.numel()
-    out = torch.zeros((n_long, n_tiles + 1), dtype=torch.int32, device=post_doc.device)   # uint32 payload
-    if n_long:
-        check(lib.fz_long_tile_offsets(_ptr(term_ptr), _ptr(post_doc), _ptr(_req(long_terms, torch.int32, "long_terms")),
-                                       n_long, tile_docs, n_tiles, _ptr(out), _stream(out)), "fz_long_tile_offsets")
     return out
 
 
@@ -357,7 +378,8 @@ def maxsim(q_tok_bf16, tok_ptr, tok_emb_bf16, cand_ids, doc_base: int = 0):
     if dim != 128 or tok_emb_bf16.shape[1] != 128:
         raise FusionB200Error("maxsim needs 128-dimensional token embeddings")
     out = torch.empty(cand_ids.shape, dtype=torch.float32, device=cand_ids.device)
+    ws = _ws(lib.fz_maxsim_workspace_bytes(nq, cand_ids.shape[1]), cand_ids.device)
     check(lib.fz_maxsim_bf16(_ptr(q_tok_bf16), lq, _ptr(cand_ids), _ptr(tok_ptr), _ptr(tok_emb_bf16),
                              tok_emb_bf16.shape[0], tok_ptr.numel() - 1, doc_base, nq, cand_ids.shape[1], _ptr(out),
-                             _stream(out)), "fz_maxsim_bf16")
+                             _ptr(ws), ws.numel(), _stream(out)), "fz_maxsim_bf16")
     return out

@@ -37,6 +37,9 @@ int fz_abi_version(void);
  * fz_profile_summary synchronises, writes one "name launches total_ms" line per kernel into out, and resets. */
 int fz_profile_enable(int on);
 int fz_profile_summary(char* out, size_t cap);
+/* Debugging aid: device buffer of [n_ctas, 8] uint64 cycle counters the persistent tensor-core kernels fill
+ * (barrier wait / issue cycles per warp role); NULL switches it off. */
+int fz_debug_set_stats(void* device_buffer);
 
 /* per-query status bits written by the top-k entry points */
 #define FZ_STATUS_OVERFLOW 1  /* candidate buffer overflowed: result for this query is NOT valid, re-run with growth=1 */
@@ -100,19 +103,39 @@ int fz_fuse(const int32_t* const* ids_h, const void* const* scores_h, const int3
  * Replaces TFIDF/BM25/AtireBM25.score + .search (src/retrievers/bm25.py:100-115,149-156) and, for SPLADE,
  * the dense [Q,V]x[V,N] cosine of src/retrievers/hybrid.py:101-103 / splade/base.py:186-197.
  * ---------------------------------------------------------------------------------------------------------- */
+/* A term's postings are stored in ONE of three forms, chosen at index time from its document frequency:
+ *   short  (df < tiled_min)        doc-ascending (doc, value) pairs plus a coarse table (postings before every 16th
+ *                                  tile): a CTA walks 16 tiles and scans the few postings between two marks
+ *   tiled  (tiled_min <= df)       per (term, doc tile) segments of (tile-relative uint16 doc offset, value), padded to
+ *                                  a multiple of 4 postings with (tile_docs, 0) so that a thread moves 4 postings with
+ *                                  one 8-byte and one 16/32-byte load; inside a segment the postings are ordered so that
+ *                                  the 32 lanes of a warp hit 32 different shared-memory banks (the order inside a
+ *                                  segment is free: a term never hits a doc twice)
+ *   dense  (df >= dense_frac * N)  one value per document (0 where the doc lacks the term): no ids, no scatter -
+ *                                  accumulated in registers with 16-byte coalesced loads                               */
 typedef struct fz_postings {
-    const int64_t* term_ptr;       /* [n_terms + 1] */
-    const int32_t* post_doc;       /* [nnz] local doc row, ascending inside a term */
-    const void* post_val;          /* [nnz] double impacts (lexical) or float weights (SPLADE) */
-    const int32_t* long_row;       /* [n_terms] row into long_tile_off, or -1 for short posting lists */
-    const uint32_t* long_tile_off; /* [n_long, n_tiles + 1] offsets (relative to term_ptr[t]) of each doc tile */
+    const int64_t* term_ptr;        /* [n_terms + 1] short lists: ranges into post_doc / post_val (empty otherwise) */
+    const int32_t* post_doc;        /* short postings: local doc row, ascending inside a term */
+    const void* post_val;           /* short postings: double impacts (lexical) or float weights (SPLADE) */
+    const uint16_t* short_coarse;   /* [n_terms, n_coarse + 1] postings of the term below tile 16 * c (rows of non-short terms unused) */
+    const int32_t* term_slot;       /* [n_terms] -1 = short, r >= 0 = tiled row r, v <= -2 = dense row (-2 - v) */
+    const int64_t* tiled_base;      /* [n_tiled] first posting of the term in tiled_off / tiled_val (multiple of 4) */
+    const uint32_t* tiled_tile_off; /* [n_tiled, n_tiles + 1] segment starts relative to tiled_base (multiples of 4) */
+    const uint16_t* tiled_off;      /* tile-relative doc offsets, == tile_docs for padding */
+    const void* tiled_val;
+    const void* dense_val;          /* [n_dense, dense_stride] */
+    int64_t dense_stride;           /* n_tiles * tile_docs */
     int32_t n_terms;
-    int32_t n_long;
-    int64_t n_docs;
-    int32_t tile_docs; /* docs per tile (multiple of 256, accumulators must fit shared memory) */
+    int32_t n_tiled;
+    int32_t n_dense;
+    int32_t tile_docs;              /* docs per shared-memory accumulator tile: multiple of 4, <= 8192 (f32) / 4096 (f64) */
     int32_t n_tiles;
+    int32_t n_coarse;               /* ceil(n_tiles / FZ_COARSE_TILES) */
+    int64_t n_docs;
 } fz_postings_t;
+#define FZ_COARSE_TILES 16 /* also the number of consecutive tiles one CTA walks */
 
+#define FZ_MAX_QUERY_TERMS 128
 #define FZ_LEX_TFIDF 0
 #define FZ_LEX_BM25 1 /* also ATIRE: only the idf table differs */
 
@@ -123,12 +146,9 @@ int fz_lexical_impacts(const int64_t* term_ptr, const int32_t* post_doc, const i
                        const double* idf, int32_t n_terms, int64_t nnz, double avgdl, double k1, double b, int variant,
                        double* out_impact, fz_stream_t stream);
 
-/* offsets of every doc tile inside the long posting lists (index build helper) */
-int fz_long_tile_offsets(const int64_t* term_ptr, const int32_t* post_doc, const int32_t* long_terms, int32_t n_long,
-                         int32_t tile_docs, int32_t n_tiles, uint32_t* out_long_tile_off, fz_stream_t stream);
-
 /* top-k: out [n_queries, k] (score desc, ties by lower doc id); zero-score docs fill up in doc-id order.
- *   q_ptr [n_queries+1], q_term [nq] (term ids in query-token order, duplicates kept, -1 = out of vocabulary),
+ *   q_ptr [n_queries+1], q_term [nq] (term ids in query-token order, duplicates kept, -1 = out of vocabulary;
+ *   at most FZ_MAX_QUERY_TERMS per query - further terms are ignored, the caller must check),
  *   q_weight [nq] float (f32 variant only; NULL => 1)
  *   growth: >= 2 geometric round growth (fast path), 1 = conservative rounds that can never overflow
  *   out_status [n_queries]: FZ_STATUS_* bits                                                              */
@@ -175,10 +195,12 @@ int fz_normalize_rows(const float* x, int64_t n_rows, int dim, int normalize, fl
  *   q_tok [n_queries * lq, 128] bf16, tok_ptr [n_docs + 1] int64, tok_emb [n_tokens, 128] bf16,
  *   cand_ids [n_queries, n_cand] global ids (ids outside [doc_base, doc_base + n_docs) are skipped, score 0)
  *   out_scores [n_queries, n_cand] fp32
+ *   ws: fz_maxsim_workspace_bytes(...) of scratch (the gathered (first token row, length) of every pair)
  * ---------------------------------------------------------------------------------------------------------- */
+size_t fz_maxsim_workspace_bytes(int n_queries, int n_cand);
 int fz_maxsim_bf16(const void* q_tok, int lq, const int32_t* cand_ids, const int64_t* tok_ptr, const void* tok_emb,
                    int64_t n_tokens, int64_t n_docs, int64_t doc_base, int n_queries, int n_cand, float* out_scores,
-                   fz_stream_t stream);
+                   void* ws, size_t ws_bytes, fz_stream_t stream);
 
 #ifdef __cplusplus
 }

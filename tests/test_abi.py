@@ -39,4 +39,6 @@ def test_argument_errors_are_reported_without_a_gpu():
 
 def test_postings_struct_matches_header_layout():
     from fusion_b200 import _lib
-    assert ctypes.sizeof(_lib.Postings) == 5 * 8 + 4 + 4 + 8 + 4 + 4
+    # fz_postings_t: 10 pointers, int64 dense_stride, 6 x int32, int64 n_docs
+    assert ctypes.sizeof(_lib.Postings) == 10 * 8 + 8 + 6 * 4 + 8
+    assert _lib.Postings.n_docs.offset == 10 * 8 + 8 + 6 * 4 and _lib.Postings.dense_stride.offset == 80

@@ -40,7 +40,7 @@ def test_lexical_golden_topk_pipeline(golden_dir, tag, cls_name, kw, k):
     from fusion_b200.retrievers import bm25 as mod
     g = np.load(os.path.join(golden_dir, "lexical_small.npz"))
     docs, queries = [str(x) for x in g["docs"]], [str(x) for x in g["queries"]]
-    r = getattr(mod, cls_name)(docs, tile_docs=256, long_min=8, **kw)
+    r = getattr(mod, cls_name)(docs, tile_docs=256, tiled_min=8, dense_frac=0.3, **kw)
     sc, ids = r.search_all_tensors(queries, top_k=k)
     assert np.array_equal(ids.cpu().numpy(), g[f"{tag}_ids"][:, :k])
     assert np.array_equal(sc.cpu().numpy(), g[f"{tag}_scores"][:, :k])
@@ -51,7 +51,7 @@ def test_lexical_c1_slice_golden(golden_dir):
     g = np.load(os.path.join(golden_dir, "lexical_c1_slice.npz"))
     (dptr, dtok), (qptr, qtok) = synth.c1_lexical(n_docs=int(g["n_docs"]), n_queries=int(g["n_queries"]))
     docs, queries = synth.ids_to_strings(dptr, dtok), synth.ids_to_strings(qptr, qtok)
-    r = BM25(docs, k1=2.5, b=0.2, tile_docs=1024, long_min=64)
+    r = BM25(docs, k1=2.5, b=0.2, tile_docs=1024, tiled_min=64)
     sc, ids = r.search_all_tensors(queries, top_k=int(g["top_k"]))
     assert np.array_equal(ids.cpu().numpy(), g["ids"])
     assert np.array_equal(sc.cpu().numpy(), g["scores"])
@@ -69,13 +69,13 @@ def _token_queries(qptr, qtok, vocab, dev):
     return torch.from_numpy(qptr.astype(np.int32)).to(dev), torch.from_numpy(t).to(dev)
 
 
-@pytest.mark.parametrize("n_docs,vocab,k,tile,cap", [(60000, 20000, 100, 8192, 8192), (30000, 500, 1000, 2048, 2048)])
+@pytest.mark.parametrize("n_docs,vocab,k,tile,cap", [(60000, 20000, 100, 4096, 8192), (30000, 500, 1000, 2048, 2048)])
 def test_bm25_c3_shaped_vs_oracle(n_docs, vocab, k, tile, cap):
     """mMARCO-shaped token statistics (k1=0.9, b=0.4) at a size the oracle finishes in seconds: bit-exact."""
     from fusion_b200 import ops
     from fusion_b200.index import LexicalIndex
     (dptr, dtok), (qptr, qtok) = synth.c3_lexical(n_docs, 48, vocab)
-    ix = LexicalIndex(dptr, dtok, vocab, "bm25", 0.9, 0.4, tile_docs=tile, long_min=256)
+    ix = LexicalIndex(dptr, dtok, vocab, "bm25", 0.9, 0.4, tile_docs=tile, tiled_min=256)
     q_ptr, q_term = _token_queries(qptr, qtok, vocab, ix.device)
     sc, ids = ops.sparse_topk(ix.view(), q_ptr, q_term, None, k, cap=cap)
     o = obm25.LexicalOracle(dptr, dtok, vocab, "bm25", 0.9, 0.4)
@@ -117,7 +117,7 @@ def test_splade_sparse_vs_dense_oracle(sim):
     vocab, n_docs, nq, k = 2000, 6000, 12, 100
     dp, dt, dw = synth.splade_vectors(n_docs, vocab, 60, 8, 200, seed=311)
     qp, qt, qw = synth.splade_vectors(nq, vocab, 12, 2, 40, seed=312)
-    ix = SparseIndex(dp, dt, dw, vocab, sim, tile_docs=1024, long_min=64)
+    ix = SparseIndex(dp, dt, dw, vocab, sim, tile_docs=1024, tiled_min=64)
     q_ptr, q_term, q_w = sparse_queries(qp, qt, qw, sim, ix.device)
     sc, ids = ops.sparse_topk(ix.view(), q_ptr, q_term, q_w, k)
     full = ops.sparse_scores(ix.view(), q_ptr, q_term, q_w).cpu()
