@@ -46,6 +46,14 @@ struct ProfScope {
     ~ProfScope() { prof_end(s); }
 };
 
+// Per-role cycle counters of the persistent tensor-core kernels (fz_debug_set_stats) are compiled in only with
+// -DFZ_KERNEL_STATS: the clock reads sit on the kernels' critical paths.
+#ifdef FZ_KERNEL_STATS
+#define FZ_CLOCK() clock64()
+#else
+#define FZ_CLOCK() 0ll
+#endif
+
 inline int num_sms() {
     static int n = 0;
     if (n == 0) {

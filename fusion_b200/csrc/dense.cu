@@ -78,7 +78,11 @@ struct GemmArgs {
     unsigned long long* stats;   // optional [gridDim.x, 8] cycle counters (fz_debug_set_stats)
 };
 
-__global__ void __launch_bounds__(kGemmThreads, 1)
+// CTA pairs (cluster of 2, adjacent query tiles, same doc tile): each CTA fetches HALF of the doc tile and multicasts it
+// to both, so the pair moves 16 + 16 KB per k-block and CTA instead of 16 + 32 KB.  The kernel is bound by L2 -> SM
+// operand traffic (profiles/), and 55 query tiles asking L2 for the same doc tile at once also miss together.
+constexpr int kPair = 2;
+__global__ void __cluster_dims__(kPair, 1, 1) __launch_bounds__(kGemmThreads, 1)
 dense_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_d,
                     const GemmArgs G) {
     extern __shared__ unsigned char smem_dyn[];
@@ -92,7 +96,11 @@ dense_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int total_tiles = G.m_tiles * G.n_tiles;
+    // tile schedule: the cluster walks (doc tile, pair of query tiles); this CTA takes query tile 2 * pair + rank
+    const int crank = (int)ptx::cluster_ctarank();
+    const int cluster_id = blockIdx.x / kPair, n_clusters = gridDim.x / kPair;
+    const int m_pairs = (G.m_tiles + kPair - 1) / kPair;
+    const int total_tiles = m_pairs * G.n_tiles;     // per cluster
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&tmap_q);
@@ -101,7 +109,7 @@ dense_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < kStages; ++i) {
             ptx::mbar_init(&full_bar[i], 1);
-            ptx::mbar_init(&empty_bar[i], 1);
+            ptx::mbar_init(&empty_bar[i], kPair);       // both CTAs of the pair must have consumed a multicast stage
         }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&tfull_bar[i], 1);
@@ -115,6 +123,7 @@ dense_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     }
     ptx::tc_fence_before();
     __syncthreads();
+    ptx::cluster_sync();                 // the partner's barriers exist before anything is multicast to them
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -124,18 +133,19 @@ dense_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             int stage = 0;
             uint32_t phase = 0;
             long long st_wait_empty = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int n_t = tile / G.m_tiles, m_t = tile - n_t * G.m_tiles;
-                const int q0 = m_t * kBM;
+            for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
+                const int n_t = tile / m_pairs, m_t = (tile - n_t * m_pairs) * kPair + crank;
+                const int q0 = m_t * kBM;       // may lie past the last query (odd tile count): TMA zero-fills
                 const long long d0 = G.r_lo + (long long)n_t * kBN;
                 for (int kb = 0; kb < G.num_k_blocks; ++kb) {
-                    const long long t0 = clock64();
+                    const long long t0 = FZ_CLOCK();
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-                    st_wait_empty += clock64() - t0;
+                    st_wait_empty += FZ_CLOCK() - t0;
                     unsigned char* sa = smem + (size_t)stage * kStageBytes;
-                    ptx::mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
+                    ptx::mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);     // own queries + both halves of the docs
                     ptx::tma_load_2d(sa, &tmap_q, &full_bar[stage], kb * kBK, q0);
-                    ptx::tma_load_2d(sa + kABytes, &tmap_d, &full_bar[stage], kb * kBK, (int32_t)d0);
+                    ptx::tma_load_2d_multicast(sa + kABytes + crank * (kBBytes / kPair), &tmap_d, &full_bar[stage], kb * kBK,
+                                               (int32_t)(d0 + crank * (kBN / kPair)), (uint16_t)((1u << kPair) - 1));
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -149,17 +159,17 @@ dense_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             uint32_t phase = 0;
             int it = 0;
             long long st_wait_tempty = 0, st_wait_full = 0, st_issue = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++it) {
                 const int buf = it & 1;
-                const long long t0 = clock64();
+                const long long t0 = FZ_CLOCK();
                 ptx::mbar_wait(&tempty_bar[buf], ((it >> 1) & 1) ^ 1);   // epilogue drained this accumulator
-                st_wait_tempty += clock64() - t0;
+                st_wait_tempty += FZ_CLOCK() - t0;
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)buf * kBN;
                 for (int kb = 0; kb < G.num_k_blocks; ++kb) {
-                    const long long t1 = clock64();
+                    const long long t1 = FZ_CLOCK();
                     ptx::mbar_wait(&full_bar[stage], phase);
-                    const long long t2 = clock64();
+                    const long long t2 = FZ_CLOCK();
                     st_wait_full += t2 - t1;
                     ptx::tc_fence_after();
                     const uint32_t sa = ptx::smem_u32(smem + (size_t)stage * kStageBytes);
@@ -170,8 +180,9 @@ dense_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                         const uint64_t db = ptx::make_smem_desc_sw128(sb + k * 32);
                         ptx::mma_bf16_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
-                    ptx::mma_commit(&empty_bar[stage]);     // smem stage reusable once these MMAs retire
-                    st_issue += clock64() - t2;
+                    // the stage is reusable once BOTH CTAs' MMAs on it have retired (either producer refills both copies)
+                    ptx::mma_commit_multicast(&empty_bar[stage], (uint16_t)((1u << kPair) - 1));
+                    st_issue += FZ_CLOCK() - t2;
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
                 ptx::mma_commit(&tfull_bar[buf]);           // accumulator complete
@@ -190,27 +201,27 @@ dense_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         const int team = (warp - 4) >> 2;
         int it = team;
         long long st_wait_tfull = 0, st_pass2 = 0, st_pass2_n = 0;
-        const long long st_begin = clock64();
+        const long long st_begin = FZ_CLOCK();
         // Every global load on this path is issued one tile ahead: under a saturated memory system a demand load
         // takes thousands of cycles and would otherwise sit between "accumulator ready" and "accumulator released".
         auto tau_of = [&](int tile) {
             if (tile >= total_tiles) return std::numeric_limits<float>::infinity();
-            const int n_t = tile / G.m_tiles, m_t = tile - n_t * G.m_tiles;
+            const int n_t = tile / m_pairs, m_t = (tile - n_t * m_pairs) * kPair + crank;
             const int q = m_t * kBM + ew * 32 + lane;
             return q < G.n_queries ? G.st.tau[q] : std::numeric_limits<float>::infinity();
         };
-        float tau_next = tau_of(blockIdx.x + team * gridDim.x);
-        for (int tile = blockIdx.x + team * gridDim.x; tile < total_tiles; tile += 2 * gridDim.x, it += 2) {
-            const int n_t = tile / G.m_tiles, m_t = tile - n_t * G.m_tiles;
+        float tau_next = tau_of(cluster_id + team * n_clusters);
+        for (int tile = cluster_id + team * n_clusters; tile < total_tiles; tile += 2 * n_clusters, it += 2) {
+            const int n_t = tile / m_pairs, m_t = (tile - n_t * m_pairs) * kPair + crank;
             const int buf = it & 1;
             const int q = m_t * kBM + ew * 32 + lane;
             const long long d0 = G.r_lo + (long long)n_t * kBN;
             const int limit = (int)min((long long)kBN, G.r_hi - d0);
             const float tau = tau_next;
-            tau_next = tau_of(tile + 2 * gridDim.x);
-            const long long t0 = clock64();
+            tau_next = tau_of(tile + 2 * n_clusters);
+            const long long t0 = FZ_CLOCK();
             ptx::mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
-            st_wait_tfull += clock64() - t0;
+            st_wait_tfull += FZ_CLOCK() - t0;
             ptx::tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)buf * kBN;
             // Pass 1: each 32-column chunk is reduced with a max TREE (no dependent chain) while the next chunk's
@@ -248,7 +259,7 @@ dense_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             // measured SLOWER: the kernel is bound by L2 -> SM operand traffic, and a team cannot start its next tile
             // before its appends have drained anyway.)
             const uint32_t wflags = __reduce_or_sync(0xffffffffu, flags);
-            const long long tp2 = clock64();
+            const long long tp2 = FZ_CLOCK();
             if (wflags) {
                 int base = total > 0 ? atomicAdd(&G.st.cnt[q], total) : 0;
                 const size_t off = (size_t)q * G.st.cap;
@@ -271,7 +282,7 @@ dense_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                         }
                     }
                 }
-                st_pass2 += clock64() - tp2;
+                st_pass2 += FZ_CLOCK() - tp2;
                 ++st_pass2_n;
             }
             ptx::tc_fence_before();
@@ -280,13 +291,14 @@ dense_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         }
         if (G.stats && ew == 0 && lane == 0 && team == 0) {
             G.stats[blockIdx.x * 8 + 4] += (unsigned long long)st_wait_tfull;
-            G.stats[blockIdx.x * 8 + 5] += (unsigned long long)(clock64() - st_begin);
+            G.stats[blockIdx.x * 8 + 5] += (unsigned long long)(FZ_CLOCK() - st_begin);
             G.stats[blockIdx.x * 8 + 6] += (unsigned long long)st_pass2;
             G.stats[blockIdx.x * 8 + 7] += (unsigned long long)st_pass2_n;
         }
     }
     ptx::tc_fence_before();
     __syncthreads();
+    ptx::cluster_sync();                 // no CTA leaves while its partner may still multicast into it
     if (warp == 2) ptx::tmem_dealloc(tmem_base, kTmemCols);
 }
 
@@ -414,7 +426,7 @@ int fz_dense_topk(const void* q_bf16, const void* d_bf16, const float* q_f32, co
     CUtensorMap tmap_q, tmap_d;
     int rc = make_bf16_tile_map(&tmap_q, q_bf16, (uint64_t)n_queries, (uint64_t)dim, kBM);
     if (rc) return rc;
-    rc = make_bf16_tile_map(&tmap_d, d_bf16, (uint64_t)n_docs, (uint64_t)dim, kBN);
+    rc = make_bf16_tile_map(&tmap_d, d_bf16, (uint64_t)n_docs, (uint64_t)dim, kBN / kPair);    // each CTA of a pair loads half
     if (rc) return rc;
     static bool attr = false;
     if (!attr) {
@@ -438,8 +450,9 @@ int fz_dense_topk(const void* q_bf16, const void* d_bf16, const float* q_f32, co
         G.r_lo = lo;
         G.r_hi = hi;
         G.n_tiles = (int)ceil_div<long long>(hi - lo, kBN);
-        const long long tiles = (long long)G.m_tiles * G.n_tiles;
-        const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+        const long long pair_tiles = (long long)ceil_div(G.m_tiles, kPair) * G.n_tiles;
+        const int max_clusters = num_sms() / kPair;
+        const int grid = kPair * (int)(pair_tiles < max_clusters ? pair_tiles : max_clusters);
         {
             ProfScope prof("dense_filter_gemm", stream);
             dense_filter_kernel<<<grid, kGemmThreads, kGemmSmem, stream>>>(tmap_q, tmap_d, G);

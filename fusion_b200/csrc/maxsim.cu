@@ -166,9 +166,9 @@ __global__ void __launch_bounds__(kMsThreads, 1) maxsim_kernel(const __grid_cons
                 [&](int, int row0, int, int R, int col, bool, bool, bool first_of_group) {
                     if (lane == 0) {
                         if (first_of_group) {
-                            const long long t0 = clock64();
+                            const long long t0 = FZ_CLOCK();
                             ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-                            st_wait_empty += clock64() - t0;
+                            st_wait_empty += FZ_CLOCK() - t0;
                         }
                         unsigned char* sb = smem_b + (size_t)stage * b_bytes + (size_t)col * 128;
                         const CUtensorMap* mp = &maps.d[R / 16 - 1];
@@ -206,11 +206,11 @@ __global__ void __launch_bounds__(kMsThreads, 1) maxsim_kernel(const __grid_cons
                 [&](int rows) {
                     if (lane == 0) {
                         const uint32_t tb = g % kMsTBufs;
-                        const long long t0 = clock64();
+                        const long long t0 = FZ_CLOCK();
                         ptx::mbar_wait(&tempty_bar[tb], ((g / kMsTBufs) & 1) ^ 1);
-                        const long long t1 = clock64();
+                        const long long t1 = FZ_CLOCK();
                         ptx::mbar_wait(&full_bar[stage], phase);
-                        const long long t2 = clock64();
+                        const long long t2 = FZ_CLOCK();
                         st_wait_tempty += t1 - t0;
                         st_wait_full += t2 - t1;
                         ptx::tc_fence_after();
@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(kMsThreads, 1) maxsim_kernel(const __grid_cons
                         }
                         ptx::mma_commit(&empty_bar[stage]);
                         ptx::mma_commit(&tfull_bar[tb]);
-                        st_issue += clock64() - t2;
+                        st_issue += FZ_CLOCK() - t2;
                     }
                     __syncwarp();
                     ++g;
@@ -254,20 +254,20 @@ __global__ void __launch_bounds__(kMsThreads, 1) maxsim_kernel(const __grid_cons
             int owner = 0;
             float m = -std::numeric_limits<float>::infinity();
             long long st_wait_tfull = 0, st_tmem = 0, st_sum = 0;
-            const long long st_begin = clock64();
+            const long long st_begin = FZ_CLOCK();
             for (int q = blockIdx.x; q < M.n_queries; q += gridDim.x) {
                 ms_walk(M, q, lane,
                     [&](int c, int, int n, int, int col, bool first_of_cand, bool last_of_cand, bool first_of_group) {
                         const uint32_t tb = g % kMsTBufs;
                         if (first_of_group) {
-                            const long long t0 = clock64();
+                            const long long t0 = FZ_CLOCK();
                             ptx::mbar_wait(&tfull_bar[tb], (g / kMsTBufs) & 1);
-                            st_wait_tfull += clock64() - t0;
+                            st_wait_tfull += FZ_CLOCK() - t0;
                             ptx::tc_fence_after();
                         }
                         if (first_of_cand) owner ^= 1;          // passages alternate between the teams; a continuation
                         if (owner != team) return;              // piece stays with the team that holds its running max
-                        const long long tq0 = clock64();
+                        const long long tq0 = FZ_CLOCK();
                         const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + tb * kMsGroupMax + (uint32_t)col;
                         // 96 columns per step (a whole passage, usually): every tcgen05.ld in flight before the one wait,
                         // four independent max chains.  A 32-column load is used only where the 16-rounded piece covers
@@ -307,14 +307,14 @@ __global__ void __launch_bounds__(kMsThreads, 1) maxsim_kernel(const __grid_cons
                             if (rem > 64) { ptx::tmem_ld_wait(rc); reduce(rc, rem - 64); }
                         }
                         m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-                        const long long tq1 = clock64();
+                        const long long tq1 = FZ_CLOCK();
                         st_tmem += tq1 - tq0;
                         if (last_of_cand) {
                             const float s = warp_sum(row_ok ? m : 0.f);
                             if (lane == 0) atomicAdd(&M.out[(size_t)q * M.n_cand + c], s);
                             m = -std::numeric_limits<float>::infinity();
                         }
-                        st_sum += clock64() - tq1;
+                        st_sum += FZ_CLOCK() - tq1;
                     },
                     [&](int) {
                         ptx::tc_fence_before();
@@ -330,7 +330,7 @@ __global__ void __launch_bounds__(kMsThreads, 1) maxsim_kernel(const __grid_cons
             if (M.stats && ew == 0 && lane == 0) {
                 if (team == 0) {
                     M.stats[blockIdx.x * 8 + 4] = (unsigned long long)st_wait_tfull;
-                    M.stats[blockIdx.x * 8 + 5] = (unsigned long long)(clock64() - st_begin);
+                    M.stats[blockIdx.x * 8 + 5] = (unsigned long long)(FZ_CLOCK() - st_begin);
                     M.stats[blockIdx.x * 8 + 6] = (unsigned long long)st_tmem;
                     M.stats[blockIdx.x * 8 + 7] = (unsigned long long)st_sum;
                 }

@@ -15,8 +15,11 @@ struct KeyBits<uint32_t> { static constexpr int hi_bits = 32; };
 template <>
 struct KeyBits<uint64_t> { static constexpr int hi_bits = 64; };
 
-// hist: 256 counters in shared memory; bcast: 2 ints in shared memory.  All threads of the CTA must call.
+// hist: 256 counters in shared memory; bcast: 4 ints in shared memory.  All threads of the CTA must call.
 // Requires 1 <= k <= n.  On return (kth_hi, kth_lo) is the k-th largest key.
+// Scores of one query share their sign and exponent bits, so whole passes fall into ONE bin: the histogram is
+// aggregated per warp (__match_any_sync) before it touches shared memory, and the passes stop as soon as the k-th
+// key's bin holds a single key (normally once the score bits are consumed - the doc-id bits only break exact ties).
 template <typename HiT>
 __device__ void cta_radix_select_kth(const HiT* __restrict__ hi, const uint32_t* __restrict__ lo, int n, int k,
                                      int* hist, int* bcast, HiT& kth_hi, uint32_t& kth_lo) {
@@ -24,22 +27,30 @@ __device__ void cta_radix_select_kth(const HiT* __restrict__ hi, const uint32_t*
     HiT p_hi = 0, m_hi = 0;          // decided prefix bits / their mask, hi word
     uint32_t p_lo = 0, m_lo = 0;     // same, lo word
     int remaining = k;
+    const int lane = threadIdx.x & 31;
     for (int shift = HB + 32 - 8; shift >= 0; shift -= 8) {
         for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
         __syncthreads();
         const bool in_hi = shift >= 32;
-        for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            const HiT h = hi[i];
-            const uint32_t l = lo[i];
-            if ((h & m_hi) == p_hi && (l & m_lo) == p_lo) {
-                const uint32_t d = in_hi ? (uint32_t)(h >> (shift - 32)) & 255u : (l >> shift) & 255u;
-                atomicAdd(&hist[d], 1);
+        for (int base = 0; base < n; base += blockDim.x) {
+            const int i = base + threadIdx.x;
+            bool match = false;
+            uint32_t d = 0;
+            if (i < n) {
+                const HiT h = hi[i];
+                const uint32_t l = lo[i];
+                match = (h & m_hi) == p_hi && (l & m_lo) == p_lo;
+                d = in_hi ? (uint32_t)(h >> (shift - 32)) & 255u : (l >> shift) & 255u;
+            }
+            const unsigned act = __ballot_sync(0xffffffffu, match);
+            if (match) {
+                const unsigned peers = __match_any_sync(act, d);
+                if (lane == __ffs(peers) - 1) atomicAdd(&hist[d], __popc(peers));
             }
         }
         __syncthreads();
         if (threadIdx.x < 32) {
             // lane l owns bins 255-8l .. 248-8l (descending); find the bin where the running count reaches `remaining`
-            const int lane = threadIdx.x;
             int c[8], s = 0;
 #pragma unroll
             for (int j = 0; j < 8; ++j) { c[j] = hist[255 - 8 * lane - j]; s += c[j]; }
@@ -57,6 +68,7 @@ __device__ void cta_radix_select_kth(const HiT* __restrict__ hi, const uint32_t*
                     if (run < remaining && remaining <= run + c[j]) {
                         bcast[0] = 255 - 8 * lane - j;      // the digit of the k-th key
                         bcast[1] = remaining - run;         // rank inside that bin
+                        bcast[2] = c[j];                    // keys in that bin
                     }
                     run += c[j];
                 }
@@ -65,6 +77,7 @@ __device__ void cta_radix_select_kth(const HiT* __restrict__ hi, const uint32_t*
         __syncthreads();
         const uint32_t d = (uint32_t)bcast[0];
         remaining = bcast[1];
+        const int in_bin = bcast[2];
         if (in_hi) {
             p_hi |= (HiT)d << (shift - 32);
             m_hi |= (HiT)255 << (shift - 32);
@@ -73,6 +86,22 @@ __device__ void cta_radix_select_kth(const HiT* __restrict__ hi, const uint32_t*
             m_lo |= 255u << shift;
         }
         __syncthreads();
+        if (in_bin == 1 && shift > 0) {
+            // the k-th key is the only key with this prefix: fetch it instead of histogramming its remaining bytes
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                const HiT h = hi[i];
+                const uint32_t l = lo[i];
+                if ((h & m_hi) == p_hi && (l & m_lo) == p_lo) {
+                    bcast[3] = i;
+                }
+            }
+            __syncthreads();
+            const int idx = bcast[3];
+            kth_hi = hi[idx];
+            kth_lo = lo[idx];
+            __syncthreads();
+            return;
+        }
     }
     kth_hi = p_hi;
     kth_lo = p_lo;

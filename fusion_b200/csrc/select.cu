@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(kSortThreads) cand_select_kernel(CandState<ST>
     uint32_t* s_lo = reinterpret_cast<uint32_t*>(s_hi + st.cap);                // [cap]
     Entry* s_sort = reinterpret_cast<Entry*>(smem_raw + align_up_dev((size_t)st.cap * (sizeof(HiT) + 4), 16));   // [k_pow2]
     __shared__ int s_hist[256];
-    __shared__ int s_bcast[2];
+    __shared__ int s_bcast[4];
     __shared__ int s_keep, s_win;
 
     const int q = blockIdx.x;
