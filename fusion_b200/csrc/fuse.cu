@@ -29,6 +29,7 @@ struct FuseParams {
     int32_t stride[FZ_FUSE_MAX_SYSTEMS];
     double weight[FZ_FUSE_MAX_SYSTEMS];
     int n_sys, n_queries, method, norm;
+    int keep_order;    // FZ_FUSE_KEEP_ORDER: one system, output in first-insertion order instead of sorted
     int table_slots;   // power of two
     int max_len;       // longest list
     int use_smem;
@@ -282,8 +283,24 @@ __global__ void __launch_bounds__(kFuseThreads) fuse_kernel(const FuseParams P) 
         __syncthreads();
     }
 
-    // gather the union into sortable records (over the dead first/last arrays), sort, write out
     const int U = s_union;
+    if (P.keep_order) {
+        // one system: first-insertion order is dense 0 .. U-1, so the (deduplicated, transformed) list is written in place
+        for (int i = threadIdx.x; i < P.out_stride; i += blockDim.x) {
+            P.out_ids[(size_t)q * P.out_stride + i] = -1;
+            P.out_scores[(size_t)q * P.out_stride + i] = -std::numeric_limits<double>::infinity();
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < H; i += blockDim.x) {
+            if (h_key[i] != kEmptyKey && h_order[i] != 0xffffffffu && (int)h_order[i] < P.out_stride) {
+                P.out_ids[(size_t)q * P.out_stride + h_order[i]] = h_key[i];
+                P.out_scores[(size_t)q * P.out_stride + h_order[i]] = h_acc[i];
+            }
+        }
+        if (threadIdx.x == 0) P.out_len[q] = min(U, P.out_stride);
+        return;
+    }
+    // gather the union into sortable records (over the dead first/last arrays), sort, write out
     int U2 = 1;
     while (U2 < U) U2 <<= 1;
     __shared__ int s_fill;
@@ -422,7 +439,10 @@ int fz_fuse(const int32_t* const* ids_h, const void* const* scores_h, const int3
             fz_stream_t stream) {
     FZ_REQUIRE(n_sys >= 1 && n_sys <= FZ_FUSE_MAX_SYSTEMS, "n_sys=%d must be in [1,%d]", n_sys, FZ_FUSE_MAX_SYSTEMS);
     FZ_REQUIRE(ids_h && scores_h && score_is_f64_h && list_stride_h && out_ids && out_scores && out_len, "null pointer");
+    const int keep_order = (method & FZ_FUSE_KEEP_ORDER) != 0;
+    method &= ~FZ_FUSE_KEEP_ORDER;
     FZ_REQUIRE(method == FZ_FUSE_BCF || method == FZ_FUSE_RRF || method == FZ_FUSE_NSF, "unknown fusion method %d", method);
+    FZ_REQUIRE(!keep_order || n_sys == 1, "FZ_FUSE_KEEP_ORDER needs exactly one system");
     FZ_REQUIRE(out_stride >= 1, "out_stride must be positive");
     if (method == FZ_FUSE_NSF) {
         FZ_REQUIRE(normalization >= FZ_NORM_NONE && normalization <= FZ_NORM_IDENTITY_F32, "unknown normalization %d", normalization);
@@ -450,6 +470,7 @@ int fz_fuse(const int32_t* const* ids_h, const void* const* scores_h, const int3
     P.n_sys = n_sys;
     P.n_queries = n_queries;
     P.method = method;
+    P.keep_order = keep_order;
     P.norm = normalization;
     fuse_plan(n_sys, list_stride_h, &P.table_slots, &P.max_len, &P.ws_per_query);
     P.use_smem = P.ws_per_query <= kFuseSmemLimit;

@@ -78,12 +78,13 @@ def rank_rows(scores: torch.Tensor, k: int, doc_base: int = 0, max_ws_bytes: int
 
 # ----------------------------------------------------------------------------------------------- K4
 def fuse(lists, method: str, normalization: str | None = None, weights=None, distributions=None,
-         out_stride: int | None = None, max_ws_bytes: int = 2 << 30):
+         out_stride: int | None = None, max_ws_bytes: int = 2 << 30, keep_order: bool = False):
     """Fuse ``S`` ranked-list systems.
 
     lists: sequence of (ids int32 [Q, n_s], scores f32|f64 [Q, n_s], lens int32 [Q] | None), rank order.
     -> (ids int32 [Q, U], scores f64 [Q, U], lens int32 [Q]); U = out_stride or sum(n_s).  Rows are the union of
-    the lists, fused score descending, ties by first insertion; padded with (-1, -inf).
+    the lists, fused score descending, ties by first insertion; padded with (-1, -inf).  ``keep_order`` (one system
+    only) returns the transformed, deduplicated list in first-insertion order instead.
     """
     lib = _lib.load()
     if method not in _lib.FUSE_METHODS:
@@ -132,12 +133,80 @@ def fuse(lists, method: str, normalization: str | None = None, weights=None, dis
         check(lib.fz_fuse(
             arr_p(*[t[lo:hi].data_ptr() for t in ids_t]), arr_p(*[t[lo:hi].data_ptr() for t in sc_t]),
             arr_p(*[0 if t is None else t[lo:hi].data_ptr() for t in len_t]), arr_i(*is64), stride_arr, s, hi - lo,
-            _lib.FUSE_METHODS[method], norm_code, arr_d(*w),
+            _lib.FUSE_METHODS[method] | (0x100 if keep_order else 0), norm_code, arr_d(*w),
             arr_p(*[d.data_ptr() for d in distr_t]) if need_distr else None,
             arr_i(*[d.numel() for d in distr_t]) if need_distr else None,
             _ptr(out_ids[lo:hi]), _ptr(out_sc[lo:hi]), _ptr(out_len[lo:hi]), u, _ptr(ws), ws.numel(), _stream(out_ids)),
             "fz_fuse")
     return out_ids, out_sc, out_len
+
+
+# ----------------------------------------------------------------------------------------------- metrics / weight sweep
+RECALL_KS = (5, 10, 20, 50, 100, 200, 500, 1000)      # run_evaluation, src/retrievers/hybrid.py:27
+MAP_KS = MRR_KS = NDCG_KS = (10, 100)
+
+
+def metric_names(recall_ks=RECALL_KS, map_ks=MAP_KS, mrr_ks=MRR_KS, ndcg_ks=NDCG_KS) -> list[str]:
+    return ([f"recall@{k}" for k in recall_ks] + [f"map@{k}" for k in map_ks] + [f"mrr@{k}" for k in mrr_ks] +
+            [f"ndcg@{k}" for k in ndcg_ks] + ["r-precision"])
+
+
+def _ks(*lists):
+    out = []
+    for ks in lists:
+        arr = (C.c_int32 * max(1, len(ks)))(*ks)
+        out += [arr, len(ks)]
+    return out
+
+
+def rank_metrics(ids: torch.Tensor, lens: torch.Tensor | None, gold_ptr: torch.Tensor, gold_ids: torch.Tensor,
+                 recall_ks=RECALL_KS, map_ks=MAP_KS, mrr_ks=MRR_KS, ndcg_ks=NDCG_KS) -> torch.Tensor:
+    """Mean retrieval metrics of ranked id lists [Q, n] against gold id lists (CSR) -> float64 [M], ``metric_names`` order
+    (src/utils/metrics.py:40-58)."""
+    lib = _lib.load()
+    ids = _req(ids, torch.int32, "ids")
+    gold_ptr = _req(gold_ptr, torch.int32, "gold_ptr")
+    gold_ids = _req(gold_ids, torch.int32, "gold_ids")
+    if lens is not None:
+        lens = _req(lens, torch.int32, "lens")
+    q, n = ids.shape
+    m = len(recall_ks) + len(map_ks) + len(mrr_ks) + len(ndcg_ks) + 1
+    out = torch.empty(m, dtype=torch.float64, device=ids.device)
+    check(lib.fz_rank_metrics(_ptr(ids), _ptr(lens), q, n, _ptr(gold_ptr), _ptr(gold_ids), *_ks(recall_ks, map_ks, mrr_ks, ndcg_ks),
+                              _ptr(out), _stream(ids)), "fz_rank_metrics")
+    return out / max(q, 1)
+
+
+def fuse_sweep(lists, normalization: str | None, weights: torch.Tensor, gold_ptr: torch.Tensor, gold_ids: torch.Tensor,
+               distributions=None, recall_ks=RECALL_KS, map_ks=MAP_KS, mrr_ks=MRR_KS, ndcg_ks=NDCG_KS) -> torch.Tensor:
+    """Linear-fusion weight sweep (src/retrievers/hybrid.py:404-426): mean metrics of the nsf fusion of ``lists`` for every
+    row of ``weights`` [W, S] -> float64 [W, M].  ``lists`` as for :func:`fuse`; each system is normalised once
+    (weight-independent), then one kernel evaluates all W weight vectors per query."""
+    lib = _lib.load()
+    s = len(lists)
+    dev = lists[0][0].device
+    q = lists[0][0].shape[0]
+    norm = [], [], []
+    for i, triple in enumerate(lists):
+        nid, nval, nlen = fuse([triple], "nsf", normalization, [1.0], None if distributions is None else [distributions[i]],
+                               keep_order=True)
+        norm[0].append(nid)
+        norm[1].append(nval)
+        norm[2].append(nlen)
+    weights = _req(torch.as_tensor(weights, dtype=torch.float64, device=dev), torch.float64, "weights")
+    if weights.dim() != 2 or weights.shape[1] != s:
+        raise FusionB200Error("weights must be [n_weights, n_systems]")
+    gold_ptr = _req(gold_ptr, torch.int32, "gold_ptr")
+    gold_ids = _req(gold_ids, torch.int32, "gold_ids")
+    m = len(recall_ks) + len(map_ks) + len(mrr_ks) + len(ndcg_ks) + 1
+    out = torch.empty((weights.shape[0], m), dtype=torch.float64, device=dev)
+    arr_p, arr_i = C.c_void_p * s, C.c_int32 * s
+    f32_path = 0 if normalization in (None, "none") else 1
+    check(lib.fz_fuse_sweep(arr_p(*[t.data_ptr() for t in norm[0]]), arr_p(*[t.data_ptr() for t in norm[1]]),
+                            arr_p(*[t.data_ptr() for t in norm[2]]), arr_i(*[t.shape[1] for t in norm[0]]), s, q, f32_path,
+                            _ptr(weights), weights.shape[0], _ptr(gold_ptr), _ptr(gold_ids),
+                            *_ks(recall_ks, map_ks, mrr_ks, ndcg_ks), _ptr(out), _stream(out)), "fz_fuse_sweep")
+    return out / max(q, 1)
 
 
 # ----------------------------------------------------------------------------------------------- K2

@@ -177,6 +177,38 @@ class Ranker:
         return order_s, torch.gather(cand_ids, 1, order_i.long())
 
 
+def weight_grid(systems: list[str], step: float = 0.05) -> list[dict[str, float]]:
+    """Every weight combination on a ``step`` grid that sums to one (hybrid.py:405-409)."""
+    import itertools
+    return [{name: float(w) for name, w in zip(systems, comb)}
+            for comb in itertools.product(np.arange(0, 1 + step, step), repeat=len(systems)) if np.isclose(sum(comb), 1.0)]
+
+
+def tune_linear_fusion_weights(results: dict[str, list[list[dict]]], labels: list[list[int]], normalization: str,
+                               step: float = 0.05, percentile_distributions: dict | None = None,
+                               device: str = "cuda") -> list[dict]:
+    """The linear-fusion weight sweep of ``hybrid.main`` (hybrid.py:404-426): one row per weight combination holding
+    ``run_evaluation``'s metrics plus ``weight_<system>`` columns, in the reference's row order.  The reference fuses
+    and evaluates once per combination (1,771 for four systems); here every system is normalised once and ONE kernel
+    evaluates all combinations per query (``fz_fuse_sweep``).  The ranked lists must be in descending score order."""
+    systems = list(results.keys())
+    host = [_lists_to_tensors(results[s], device) for s in systems]
+    lists = [(torch.from_numpy(h[0].astype(np.int32)).to(device), torch.from_numpy(h[1]).to(device),
+              torch.from_numpy(h[2]).to(device)) for h in host]
+    combos = weight_grid(systems, step)
+    w = torch.tensor([[c[s] for s in systems] for c in combos], dtype=torch.float64, device=device)
+    gp = np.zeros(len(labels) + 1, dtype=np.int32)
+    np.cumsum([len(g) for g in labels], out=gp[1:])
+    gi = np.fromiter((int(x) for g in labels for x in g), dtype=np.int64, count=int(gp[-1])).astype(np.int32)
+    distrs = None
+    if normalization in ('percentile-rank', 'normal-curve-equivalent'):
+        distrs = [np.asarray(percentile_distributions.get(s), dtype=np.float64) for s in systems]
+    vals = ops.fuse_sweep(lists, normalization, w, torch.from_numpy(gp).to(device), torch.from_numpy(gi).to(device),
+                          distrs).cpu().numpy()
+    names = ops.metric_names()
+    return [{**dict(zip(names, row.tolist())), **{f'weight_{k}': v for k, v in c.items()}} for row, c in zip(vals, combos)]
+
+
 class Aggregator:
     """Aggregating ranked lists (hybrid.py:166-307)."""
 

@@ -82,6 +82,8 @@ int fz_rank_rows_f64(const double* scores, int n_queries, int64_t n_docs, int k,
 #define FZ_FUSE_BCF 0
 #define FZ_FUSE_RRF 1
 #define FZ_FUSE_NSF 2
+#define FZ_FUSE_KEEP_ORDER 0x100 /* OR into `method`, one system only: the transformed, deduplicated list in first-insertion
+                                  order instead of sorted (the per-system normalisation step of fz_fuse_sweep) */
 #define FZ_NORM_NONE 0
 #define FZ_NORM_MINMAX 1
 #define FZ_NORM_ZSCORE 2
@@ -97,6 +99,31 @@ int fz_fuse(const int32_t* const* ids_h, const void* const* scores_h, const int3
             int normalization, const double* weights_h, const float* const* distr_h, const int32_t* distr_len_h,
             int32_t* out_ids, double* out_scores, int32_t* out_len, int out_stride, void* ws, size_t ws_bytes,
             fz_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Evaluation next to the path.
+ * fz_rank_metrics: recall@k / map@k / mrr@k / ndcg@k / R-precision of ranked id lists against gold id lists, SUMMED over
+ * the queries (divide by n_queries for Metrics.compute_all_metrics, src/utils/metrics.py:40-162; the metric set of
+ * run_evaluation, src/retrievers/hybrid.py:24-27, is recall {5,10,20,50,100,200,500,1000}, map/mrr/ndcg {10,100}).
+ *   ids [n_queries, stride] (-1 padded), lens [n_queries] or NULL, gold_ptr [n_queries + 1], gold_ids: device memory
+ *   *_k_h: host arrays of cut-offs (at most 8 each); at most 64 distinct gold ids per query are used
+ *   out_sum: device doubles [n_recall + n_map + n_mrr + n_ndcg + 1] in that order, R-precision last
+ * fz_fuse_sweep: the linear-fusion weight sweep of src/retrievers/hybrid.py:404-426 - for every weight vector, fuse the
+ * systems' lists by weighted sum (union, missing = 0, stable descending order) and evaluate; out_sum [n_weights, M].
+ *   ids_h[s] / vals_h[s]: host arrays of device pointers to the ALREADY NORMALISED lists [n_queries, list_stride[s]] without
+ *   repeated ids (fz_fuse on the single system with weight 1 produces exactly that); values_are_f32 = 1 when the values
+ *   are fp32 numbers (any torch normalisation; summed in fp32 like the reference), 0 for normalization 'none' (fp64);
+ *   weights: device doubles [n_weights, n_sys].  The union of one query's lists must fit shared memory (top-k lists).
+ * ---------------------------------------------------------------------------------------------------------- */
+int fz_rank_metrics(const int32_t* ids, const int32_t* lens, int n_queries, int stride, const int32_t* gold_ptr,
+                    const int32_t* gold_ids, const int32_t* recall_k_h, int n_recall, const int32_t* map_k_h, int n_map,
+                    const int32_t* mrr_k_h, int n_mrr, const int32_t* ndcg_k_h, int n_ndcg, double* out_sum,
+                    fz_stream_t stream);
+int fz_fuse_sweep(const int32_t* const* ids_h, const double* const* vals_h, const int32_t* const* lens_h,
+                  const int32_t* list_stride_h, int n_sys, int n_queries, int values_are_f32, const double* weights,
+                  int n_weights, const int32_t* gold_ptr, const int32_t* gold_ids, const int32_t* recall_k_h, int n_recall,
+                  const int32_t* map_k_h, int n_map, const int32_t* mrr_k_h, int n_mrr, const int32_t* ndcg_k_h, int n_ndcg,
+                  double* out_sum, fz_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * K2  sparse scoring over a term-major CSR inverted index, document range tiled for shared-memory accumulators.

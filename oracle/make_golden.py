@@ -118,6 +118,48 @@ def golden_fusion():
     np.savez_compressed(os.path.join(OUT, "fusion_small.npz"), **out)
 
 
+def golden_sweep():
+    """Weight sweep + metrics, verbatim: Aggregator.fuse per weight vector (hybrid.py:404-426) and Metrics with
+    run_evaluation's configuration (hybrid.py:24-27, utils/metrics.py)."""
+    import copy
+    import importlib
+    import itertools
+    mod = ref_loader.load_hybrid()
+    metrics_mod = importlib.import_module("src.utils.metrics")
+    rng = np.random.Generator(np.random.PCG64(23))
+    n_q, n, pool = 8, 40, 90
+    lists = {"bm25": _ranked_lists(rng, n_q, n, pool, dup=True), "dpr": _ranked_lists(rng, n_q, n - 5, pool),
+             "splade": _ranked_lists(rng, n_q, n, pool)}
+    for q in lists["dpr"]:
+        for x in q:
+            x["score"] = float(np.float32(x["score"] * 0.01))
+    golds = [sorted(rng.choice(pool, size=int(rng.integers(1, 6)), replace=False).tolist()) for _ in range(n_q)]
+    golds[2] = [pool + 5]                  # a query whose only relevant doc is never retrieved
+    step = 0.25
+    combos = [comb for comb in itertools.product(np.arange(0, 1 + step, step), repeat=len(lists)) if np.isclose(sum(comb), 1.0)]
+    evaluator = metrics_mod.Metrics(recall_at_k=[5, 10, 20, 50, 100, 200, 500, 1000], map_at_k=[10, 100], mrr_at_k=[10, 100],
+                                    ndcg_at_k=[10, 100])
+    out = {"systems": np.array(list(lists)), "weights": np.array(combos, dtype=np.float64),
+           "gold_ptr": np.cumsum([0] + [len(g) for g in golds]).astype(np.int32),
+           "gold_ids": np.concatenate(golds).astype(np.int32)}
+    for k, v in lists.items():
+        out[f"in_ids_{k}"] = np.array([[x["corpus_id"] for x in q] for q in v], dtype=np.int32)
+        out[f"in_scores_{k}"] = np.array([[x["score"] for x in q] for q in v], dtype=np.float64)
+    names = None
+    for norm in ("min-max", "z-score", "none"):
+        rows = []
+        for comb in combos:
+            weights = {name: w for name, w in zip(lists, comb)}
+            ranked = mod.Aggregator.fuse(copy.deepcopy(lists), method="nsf", normalization=norm, linear_weights=weights,
+                                         percentile_distributions={})
+            sc = evaluator.compute_all_metrics(all_ground_truths=golds, all_results=[[x["corpus_id"] for x in r] for r in ranked])
+            names = list(sc)
+            rows.append([float(sc[m]) for m in names])
+        out[f"metrics_{norm}"] = np.array(rows, dtype=np.float64)
+    out["metric_names"] = np.array(names)
+    np.savez_compressed(os.path.join(OUT, "sweep_small.npz"), **out)
+
+
 def golden_dense():
     q = torch.from_numpy(synth.dense_embeddings(7, 64, seed=31))
     d = torch.from_numpy(synth.dense_embeddings(3000, 64, seed=32))
@@ -135,6 +177,7 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     golden_lexical()
     golden_fusion()
+    golden_sweep()
     golden_dense()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -130,3 +130,67 @@ def test_fuse_ragged_and_float32_inputs():
         got = np.asarray(sc[qi, :n].cpu())
         exp = np.asarray(esc, dtype=np.float64)
         np.testing.assert_allclose(got, exp, rtol=1e-5, atol=1e-5, equal_nan=True)
+
+
+# ------------------------------------------------------------------------------------------------ metrics + weight sweep
+def _sweep_fixture(golden_dir):
+    g = np.load(os.path.join(golden_dir, "sweep_small.npz"))
+    systems = [str(s) for s in g["systems"]]
+    nq = g[f"in_ids_{systems[0]}"].shape[0]
+    results = {k: [[{"corpus_id": int(i), "score": float(s)} for i, s in zip(g[f"in_ids_{k}"][q], g[f"in_scores_{k}"][q])]
+                   for q in range(nq)] for k in systems}
+    gp, gi = g["gold_ptr"], g["gold_ids"]
+    golds = [gi[gp[i]:gp[i + 1]].tolist() for i in range(nq)]
+    return g, systems, results, golds
+
+
+@pytest.mark.parametrize("norm", ["min-max", "z-score", "none"])
+def test_weight_sweep_matches_reference(golden_dir, norm):
+    """hybrid.py:404-426 executed verbatim (Aggregator.fuse + Metrics per weight vector) vs ONE fz_fuse_sweep launch."""
+    from fusion_b200.retrievers.hybrid import tune_linear_fusion_weights, weight_grid
+    g, systems, results, golds = _sweep_fixture(golden_dir)
+    rows = tune_linear_fusion_weights(results, golds, norm, step=0.25)
+    assert len(rows) == g["weights"].shape[0]
+    names = [str(x) for x in g["metric_names"]]
+    for r, w, exp in zip(rows, g["weights"], g[f"metrics_{norm}"]):
+        assert [r[f"weight_{k}"] for k in systems] == w.tolist()
+        np.testing.assert_allclose([r[n] for n in names], exp, rtol=1e-12, atol=1e-12)
+    assert len(weight_grid(["a", "b", "c", "d"], 0.05)) == 1771          # the reference's four-system grid
+
+
+def test_metrics_class_matches_reference(golden_dir):
+    """Metrics.compute_all_metrics on fused rankings == the reference's values for the same rankings."""
+    from fusion_b200.retrievers.hybrid import Aggregator
+    from fusion_b200.utils.metrics import Metrics
+    g, systems, results, golds = _sweep_fixture(golden_dir)
+    w = g["weights"][5]
+    ranked = Aggregator.fuse(results, method="nsf", normalization="z-score", linear_weights=dict(zip(systems, w.tolist())))
+    ev = Metrics(recall_at_k=[5, 10, 20, 50, 100, 200, 500, 1000], map_at_k=[10, 100], mrr_at_k=[10, 100], ndcg_at_k=[10, 100])
+    sc = ev.compute_all_metrics(golds, [[x["corpus_id"] for x in r] for r in ranked])
+    names = [str(x) for x in g["metric_names"]]
+    np.testing.assert_allclose([sc[n] for n in names], g["metrics_z-score"][5], rtol=1e-12, atol=1e-12)
+    # per-query helpers against the oracle restatement
+    from oracle import metrics as om
+    res0 = [x["corpus_id"] for x in ranked[0]]
+    exp = om.query_metrics(golds[0], res0)
+    assert abs(ev.recall(golds[0], res0, 10) - exp[1]) < 1e-12
+    assert abs(ev.average_precision(golds[0], res0, 100) - exp[9]) < 1e-12
+    assert abs(ev.ndcg(golds[0], res0, 10) - exp[12]) < 1e-12
+    assert abs(ev.r_precision(golds[0], res0) - exp[14]) < 1e-12
+    with pytest.raises(ZeroDivisionError):
+        ev.compute_all_metrics([[]], [[1, 2]])
+
+
+def test_metrics_oracle_random_vs_kernel():
+    from fusion_b200 import ops
+    from oracle import metrics as om
+    rng = np.random.Generator(np.random.PCG64(5))
+    nq, n = 40, 300
+    ids = np.stack([rng.permutation(1000)[:n] for _ in range(nq)]).astype(np.int32)
+    golds = [rng.choice(1000, size=int(rng.integers(1, 9)), replace=False).tolist() for _ in range(nq)]
+    golds[3] = golds[3] + golds[3][:1]                 # a duplicated gold id counts twice in len(gold) only
+    gp = np.cumsum([0] + [len(g) for g in golds]).astype(np.int32)
+    gi = np.concatenate(golds).astype(np.int32)
+    got = ops.rank_metrics(torch.from_numpy(ids).cuda(), None, torch.from_numpy(gp).cuda(), torch.from_numpy(gi).cuda())
+    exp = om.mean_metrics(golds, [r.tolist() for r in ids])
+    np.testing.assert_allclose(got.cpu().numpy(), exp, rtol=1e-12, atol=1e-12)

@@ -82,3 +82,22 @@ def test_dense_small(golden_dir, sim):
         # tensor form: same scores to fp32 rounding, same id set
         np.testing.assert_allclose(sc[qi].numpy(), g[f"{sim}_scores"][qi], rtol=2e-6, atol=2e-6)
         assert sorted(ids[qi].tolist()) == sorted(g[f"{sim}_ids"][qi].tolist())
+
+
+def test_metrics_and_sweep_oracle_match_verbatim_reference(golden_dir):
+    """oracle/metrics.py against Aggregator.fuse + Metrics executed verbatim for every weight vector (hybrid.py:404-426)."""
+    import os
+    import numpy as np
+    from oracle import metrics as om
+    g = np.load(os.path.join(golden_dir, "sweep_small.npz"))
+    systems = [str(s) for s in g["systems"]]
+    nq = g[f"in_ids_{systems[0]}"].shape[0]
+    ids = [[g[f"in_ids_{k}"][q] for q in range(nq)] for k in systems]
+    sc = [[g[f"in_scores_{k}"][q] for q in range(nq)] for k in systems]
+    gp, gi = g["gold_ptr"], g["gold_ids"]
+    golds = [gi[gp[i]:gp[i + 1]].tolist() for i in range(nq)]
+    assert [str(x) for x in g["metric_names"]] == om.metric_names()
+    assert [tuple(w) for w in g["weights"]] == om.weight_grid(len(systems), 0.25)
+    for norm in ("min-max", "z-score", "none"):
+        got = np.array(om.sweep(ids, sc, golds, [tuple(w) for w in g["weights"]], norm))
+        assert np.array_equal(got, g[f"metrics_{norm}"]), norm
