@@ -209,16 +209,16 @@ def cpu_reference_sample(n_docs_full, n_queries_full, systems, seconds_budget=25
     per_q, sample = {}, {}
     if "bm25" in systems:
         n = 200_000
-        (dptr, dtok), (qptr, qtok) = synth.c3_lexical(n, 8, BM25_VOCAB)
+        (dptr, dtok), (qptr, qtok) = synth.c3_lexical(n, 16, BM25_VOCAB)
         o = obm25.LexicalOracle(dptr, dtok, BM25_VOCAB, "bm25", 0.9, 0.4)
         t0 = time.perf_counter()
-        for qi in range(8):
+        for qi in range(16):
             t = qtok[qptr[qi]:qptr[qi + 1]]
             o.search_ids(np.where(t < BM25_VOCAB, t, -1), TOP_K)
-        per_q["bm25"] = (time.perf_counter() - t0) / 8 * (n_docs_full / n)
-        sample["bm25"] = f"8 queries x {n} docs (numpy port of bm25.py:100-156), scaled x{n_docs_full / n:.1f} in N"
+        per_q["bm25"] = (time.perf_counter() - t0) / 16 * (n_docs_full / n)
+        sample["bm25"] = f"16 queries x {n} docs (numpy port of bm25.py:100-156), scaled x{n_docs_full / n:.1f} in N"
     if "dpr" in systems:
-        n, nq = 500_000, 16
+        n, nq = 500_000, 64
         d = torch.nn.functional.normalize(torch.randn(n, DIM), dim=1)
         q = torch.randn(nq, DIM)
         t0 = time.perf_counter()
@@ -227,7 +227,7 @@ def cpu_reference_sample(n_docs_full, n_queries_full, systems, seconds_budget=25
         sample["dpr"] = f"{nq} queries x {n} docs x {DIM} in 50k-doc chunks (torch CPU sgemm + topk), scaled x{n_docs_full / n:.1f}"
         del d
     if "splade" in systems:
-        n, nq = 20_000, 8
+        n, nq = 20_000, 32
         dp, dt, dw = synth.splade_vectors(n, SPLADE_VOCAB, 120, 8, 512, seed=311)
         qp, qt, qw = synth.splade_vectors(nq, SPLADE_VOCAB, 24, 2, 64, seed=312)
         dd = torch.from_numpy(synth.densify(dp, dt, dw, SPLADE_VOCAB))

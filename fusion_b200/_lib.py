@@ -49,6 +49,9 @@ SIGNATURES = {
     "fz_fuse": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _i, _p, _sz, _p]),
     "fz_rank_metrics": (_i, [_p, _p, _i, _i, _p, _p, _p, _i, _p, _i, _p, _i, _p, _i, _p, _p]),
     "fz_fuse_sweep": (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _i, _p, _p, _p, _i, _p, _i, _p, _i, _p, _i, _p, _p]),
+    "fz_token_starts": (_i, [_p, _i64, _p, _p]),
+    "fz_hash_tokens": (_i, [_p, _i64, _p, _i64, _p, _p, _p, _p]),
+    "fz_quantiles_f64": (_i, [_p, _i64, _i, _p, _p]),
     "fz_lexical_impacts": (_i, [_p, _p, _p, _p, _p, C.c_int32, _i64, _d, _d, _d, _i, _p, _p]),
     "fz_sparse_topk_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "fz_sparse_topk_f64": (_i, [_p, _p, _p, _i, _i, _i64, _i, _i, _i, _p, _p, _p, _p, _sz, _p]),

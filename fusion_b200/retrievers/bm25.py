@@ -27,13 +27,23 @@ class TFIDF:
     """TF-IDF retrieval model (bm25.py:33-126)."""
     _variant = "tfidf"
 
-    def __init__(self, corpus: list[str], device: str = "cuda", **index_kwargs):
+    def __init__(self, corpus: list[str], device: str = "cuda", device_tokenizer: bool = False, **index_kwargs):
         self.corpus = corpus
         self.corpus_size = len(corpus)
-        self._vocab, doc_ptr, doc_tok = self._tokenize(corpus)
-        self.index = LexicalIndex(doc_ptr, doc_tok, len(self._vocab), variant=self._variant,
+        self._device_vocab = None
+        if device_tokenizer:
+            # tokenise on the device (fusion_b200.text): no per-word Python loop; the vocabulary is a sorted hash table,
+            # so the string-keyed views (`vocab`, `df`, `idf`) are not available in this mode
+            from .. import text
+            self._device_vocab, doc_ptr, doc_tok = text.tokenize_corpus(corpus, device)
+            self._vocab = None
+            n_terms = len(self._device_vocab)
+        else:
+            self._vocab, doc_ptr, doc_tok = self._tokenize(corpus)
+            n_terms = len(self._vocab)
+        self.index = LexicalIndex(doc_ptr, doc_tok, n_terms, variant=self._variant,
                                   k1=getattr(self, "k1", 0.0), b=getattr(self, "b", 0.0), device=device, **index_kwargs)
-        self.doc_len = np.diff(doc_ptr).tolist()
+        self.doc_len = self.index.doc_len.cpu().tolist()
         self.avgdl = self.index.avgdl
 
     def __repr__(self):
@@ -73,6 +83,9 @@ class TFIDF:
 
     # -- queries
     def _encode_queries(self, queries: list[str]):
+        if self._device_vocab is not None:
+            from .. import text
+            return text.tokenize_queries(queries, self._device_vocab, self.index.device)
         ptr = np.zeros(len(queries) + 1, dtype=np.int32)
         toks: list[int] = []
         for i, q in enumerate(queries):

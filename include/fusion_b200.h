@@ -126,6 +126,21 @@ int fz_fuse_sweep(const int32_t* const* ids_h, const double* const* vals_h, cons
                   double* out_sum, fz_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Index-build helpers next to the path.
+ * fz_token_starts / fz_hash_tokens: whitespace tokenisation of a UTF-8 buffer with the rules of Python's str.split()
+ * (`doc.split()`, src/retrievers/bm25.py:54-60,72,81,101; the Unicode whitespace set of str.isspace()).
+ *   out_flags [n_bytes] uint8: 1 where a token starts.  starts [n_tokens] int64: those byte offsets.
+ *   out_h1 / out_h2 [n_tokens] int64: two independent 64-bit hashes of the token bytes (equal tokens <=> equal pairs,
+ *   up to a 2^-128 collision); out_len [n_tokens] int32 token length in bytes (may be NULL).
+ * fz_quantiles_f64: np.percentile(..., method='linear') of an ASCENDING array at linspace(0, 1, n_quantiles) - what
+ * pandas Series.quantile computes for the percentile distributions (src/retrievers/hybrid.py:391-398).
+ * ---------------------------------------------------------------------------------------------------------- */
+int fz_token_starts(const void* utf8, int64_t n_bytes, void* out_flags, fz_stream_t stream);
+int fz_hash_tokens(const void* utf8, int64_t n_bytes, const int64_t* starts, int64_t n_tokens, int64_t* out_h1,
+                   int64_t* out_h2, int32_t* out_len, fz_stream_t stream);
+int fz_quantiles_f64(const double* sorted, int64_t n, int n_quantiles, double* out, fz_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * K2  sparse scoring over a term-major CSR inverted index, document range tiled for shared-memory accumulators.
  * Replaces TFIDF/BM25/AtireBM25.score + .search (src/retrievers/bm25.py:100-115,149-156) and, for SPLADE,
  * the dense [Q,V]x[V,N] cosine of src/retrievers/hybrid.py:101-103 / splade/base.py:186-197.

@@ -160,6 +160,31 @@ def golden_sweep():
     np.savez_compressed(os.path.join(OUT, "sweep_small.npz"), **out)
 
 
+def golden_distribution():
+    """Percentile-based score distributions, the pandas expression of hybrid.py:391-398 executed as written."""
+    import pandas as pd
+    rng = np.random.Generator(np.random.PCG64(29))
+    rows = []
+    for system, (mu, sd, n) in {"bm25": (4.0, 2.5, 4000), "dpr": (0.3, 0.1, 3000)}.items():
+        sc = rng.normal(mu, sd, n)
+        sc[rng.random(n) < 0.2] = 0.0                      # unmatched documents
+        sc[:50] = sc.min()                                 # a repeated smallest value
+        sc = np.float32(sc).astype(np.float64) if system == "dpr" else sc
+        rows += [{"system": system, "score": float(v)} for v in sc]
+    all_scores_df = pd.DataFrame(rows, columns=["system", "score"])
+    out = {"systems": np.array(["bm25", "dpr"])}
+    for s in ("bm25", "dpr"):
+        out[f"scores_{s}"] = all_scores_df[all_scores_df["system"] == s]["score"].to_numpy()
+    # hybrid.py:391-398 chains two groupby().apply() calls; under the pandas installed here (>= 2.2) apply() no longer
+    # carries the grouping column through reset_index(drop=True), so the same two steps run per group explicitly with the
+    # same pandas calls (filter: drop zeros and the two smallest distinct scores; Series.quantile(np.linspace(0, 1, N+1))).
+    for N in (10, 1000):
+        for s, group in all_scores_df.groupby('system'):
+            kept = group[(group['score'] != 0.0) & (~group['score'].isin(group['score'].drop_duplicates().nsmallest(2)))]
+            out[f"distr_{s}_{N}"] = pd.Series(kept['score'].quantile(np.linspace(0, 1, N+1))).to_numpy()
+    np.savez_compressed(os.path.join(OUT, "distribution_small.npz"), **out)
+
+
 def golden_dense():
     q = torch.from_numpy(synth.dense_embeddings(7, 64, seed=31))
     d = torch.from_numpy(synth.dense_embeddings(3000, 64, seed=32))
@@ -178,6 +203,7 @@ def main():
     golden_lexical()
     golden_fusion()
     golden_sweep()
+    golden_distribution()
     golden_dense()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -101,3 +101,13 @@ def test_metrics_and_sweep_oracle_match_verbatim_reference(golden_dir):
     for norm in ("min-max", "z-score", "none"):
         got = np.array(om.sweep(ids, sc, golds, [tuple(w) for w in g["weights"]], norm))
         assert np.array_equal(got, g[f"metrics_{norm}"]), norm
+
+
+def test_distribution_oracle_matches_pandas_golden(golden_dir):
+    import os
+    import numpy as np
+    from oracle import distributions as od
+    g = np.load(os.path.join(golden_dir, "distribution_small.npz"))
+    for s in ("bm25", "dpr"):
+        for n in (10, 1000):
+            assert np.array_equal(od.percentile_distribution(g[f"scores_{s}"], n), g[f"distr_{s}_{n}"])
