@@ -52,6 +52,7 @@ void prof_end(cudaStream_t stream) {
 }
 
 constexpr int kSortThreads = 1024;
+constexpr int kSelectThreads = 512;     // cand_select: two CTAs per SM (registers and shared memory) overlap each other's barriers
 constexpr int kSmemEntries = 8192;   // 128 KB
 constexpr int kChunk = 4096;         // chunk staged through smem by the large sort
 
@@ -146,7 +147,7 @@ __device__ __forceinline__ void hi_score(uint32_t h, float& s) { s = unord32(h);
 __device__ __forceinline__ void hi_score(uint64_t h, double& s) { s = unord64(h); }
 
 template <typename ST>
-__global__ void __launch_bounds__(kSortThreads) cand_select_kernel(CandState<ST> st, int k, ST margin, int final_out,
+__global__ void __launch_bounds__(kSelectThreads, 2) cand_select_kernel(CandState<ST> st, int k, ST margin, int final_out,
                                                                    long long doc_base, ST* out_scores,
                                                                    int32_t* out_ids, int32_t* out_n, int k_pow2) {
     using HiT = typename HiOf<ST>::type;
@@ -187,20 +188,38 @@ __global__ void __launch_bounds__(kSortThreads) cand_select_kernel(CandState<ST>
     // survivors: exactly the k best when margin == 0 (a later doc that only ties the k-th score loses the tie:
     // rounds visit docs in ascending id order), everything with score >= tau otherwise; all records if n < k
     const HiT tau_hi = (HiT)score_key(tau);
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const HiT h = s_hi[i];
-        const uint32_t l = s_lo[i];
-        const bool win = !full || key_ge<HiT>(h, l, kth_hi, kth_lo);
-        const bool keep = !full || (margin == (ST)0 ? win : h >= tau_hi);
+    // compaction: one shared-memory atomic per warp (ballot + prefix), not one per record on a single counter
+    const int lane = threadIdx.x & 31;
+    for (int base = 0; base < n; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        HiT h = 0;
+        uint32_t l = 0;
+        bool win = false, keep = false;
+        if (i < n) {
+            h = s_hi[i];
+            l = s_lo[i];
+            win = !full || key_ge<HiT>(h, l, kth_hi, kth_lo);
+            keep = !full || (margin == (ST)0 ? win : h >= tau_hi);
+        }
+        const unsigned bk = __ballot_sync(0xffffffffu, keep);
+        const unsigned bw = __ballot_sync(0xffffffffu, final_out && win);
+        int pk = 0, pw = 0;
+        if (lane == 0) {
+            if (bk) pk = atomicAdd(&s_keep, __popc(bk));
+            if (bw) pw = atomicAdd(&s_win, __popc(bw));
+        }
+        pk = __shfl_sync(0xffffffffu, pk, 0);
+        pw = __shfl_sync(0xffffffffu, pw, 0);
+        const unsigned below = (1u << lane) - 1;
         if (keep) {
-            const int p = atomicAdd(&s_keep, 1);
+            const int p = pk + __popc(bk & below);
             ST s;
             hi_score(h, s);
             st.score[off + p] = s;
             st.id[off + p] = (int32_t)~l;
         }
         if (final_out && win) {
-            const int p = atomicAdd(&s_win, 1);
+            const int p = pw + __popc(bw & below);
             Entry e;
             e.skey = (uint64_t)h;
             e.tie = l;
@@ -254,10 +273,12 @@ int cand_select(const CandState<ST>& st, int n_queries, int k, ST margin, bool f
     bool& done = std::is_same<ST, float>::value ? attr_f : attr_d;
     if (!done) {
         FZ_CUDA(cudaFuncSetAttribute(cand_select_kernel<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        FZ_CUDA(cudaFuncSetAttribute(cand_select_kernel<ST>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     cudaSharedmemCarveoutMaxShared));
         done = true;
     }
     ProfScope prof(std::is_same<ST, float>::value ? "cand_select_f32" : "cand_select_f64", stream);
-    cand_select_kernel<ST><<<n_queries, kSortThreads, smem, stream>>>(st, k, margin, final_out ? 1 : 0,
+    cand_select_kernel<ST><<<n_queries, kSelectThreads, smem, stream>>>(st, k, margin, final_out ? 1 : 0,
                                                                       (long long)doc_base, out_scores, out_ids, out_n,
                                                                       k_pow2);
     FZ_LAUNCH_CHECK();
