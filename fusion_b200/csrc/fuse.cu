@@ -10,6 +10,7 @@
 // The table lives in shared memory when it fits (4 systems x 1000 candidates) and in a global workspace otherwise
 // (the reference's full-length lists, n = N).
 #include "common.cuh"
+#include "radix_select.cuh"
 
 #include <limits>
 
@@ -318,6 +319,42 @@ __global__ void __launch_bounds__(kFuseThreads) fuse_kernel(const FuseParams P) 
         }
     }
     __syncthreads();
+    // Only the best out_stride entries are written: when that is less than the union, pick them with a radix select over
+    // (fused score, first insertion) and sort just those - the sort network is the shared-memory-bound part of the kernel.
+    if (P.use_smem && P.out_stride < U && (size_t)P.out_stride * sizeof(Entry) <= (size_t)H * 8) {
+        __shared__ int s_hist[256];
+        __shared__ int s_bc[4];
+        __shared__ int s_nwin;
+        uint64_t kth_hi = 0;
+        uint32_t kth_lo = 0;
+        const Entry* src = sort_buf;
+        cta_radix_select_kth_by<uint64_t>([src](int i) { return src[i].skey; }, [src](int i) { return src[i].tie; }, U,
+                                          P.out_stride, s_hist, s_bc, kth_hi, kth_lo);
+        Entry* win = reinterpret_cast<Entry*>(h_acc);     // the accumulators are dead once the records are gathered
+        if (threadIdx.x == 0) s_nwin = 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < U; i += blockDim.x) {
+            const Entry e = sort_buf[i];
+            if (key_ge<uint64_t>(e.skey, e.tie, kth_hi, kth_lo)) win[atomicAdd(&s_nwin, 1)] = e;
+        }
+        __syncthreads();
+        const int m = s_nwin;                             // == out_stride (keys are unique)
+        int m2 = 1;
+        while (m2 < m) m2 <<= 1;
+        for (int i = m + threadIdx.x; i < m2; i += blockDim.x) {
+            Entry e;
+            e.skey = 0; e.tie = 0; e.payload = 0;
+            win[i] = e;
+        }
+        __syncthreads();
+        bitonic_sort_cta(win, m2);
+        for (int i = threadIdx.x; i < P.out_stride; i += blockDim.x) {
+            P.out_ids[(size_t)q * P.out_stride + i] = i < m ? (int32_t)win[i].payload : -1;
+            P.out_scores[(size_t)q * P.out_stride + i] = i < m ? unord64(win[i].skey) : -std::numeric_limits<double>::infinity();
+        }
+        if (threadIdx.x == 0) P.out_len[q] = m;
+        return;
+    }
     for (int i = U + threadIdx.x; i < U2; i += blockDim.x) {
         Entry e;
         e.skey = 0; e.tie = 0; e.payload = 0;

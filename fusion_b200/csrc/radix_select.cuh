@@ -20,9 +20,9 @@ struct KeyBits<uint64_t> { static constexpr int hi_bits = 64; };
 // Scores of one query share their sign and exponent bits, so whole passes fall into ONE bin: the histogram is
 // aggregated per warp (__match_any_sync) before it touches shared memory, and the passes stop as soon as the k-th
 // key's bin holds a single key (normally once the score bits are consumed - the doc-id bits only break exact ties).
-template <typename HiT>
-__device__ void cta_radix_select_kth(const HiT* __restrict__ hi, const uint32_t* __restrict__ lo, int n, int k,
-                                     int* hist, int* bcast, HiT& kth_hi, uint32_t& kth_lo) {
+template <typename HiT, typename GetHi, typename GetLo>
+__device__ void cta_radix_select_kth_by(GetHi get_hi, GetLo get_lo, int n, int k, int* hist, int* bcast, HiT& kth_hi,
+                                        uint32_t& kth_lo) {
     constexpr int HB = KeyBits<HiT>::hi_bits;
     HiT p_hi = 0, m_hi = 0;          // decided prefix bits / their mask, hi word
     uint32_t p_lo = 0, m_lo = 0;     // same, lo word
@@ -37,8 +37,8 @@ __device__ void cta_radix_select_kth(const HiT* __restrict__ hi, const uint32_t*
             bool match = false;
             uint32_t d = 0;
             if (i < n) {
-                const HiT h = hi[i];
-                const uint32_t l = lo[i];
+                const HiT h = get_hi(i);
+                const uint32_t l = get_lo(i);
                 match = (h & m_hi) == p_hi && (l & m_lo) == p_lo;
                 d = in_hi ? (uint32_t)(h >> (shift - 32)) & 255u : (l >> shift) & 255u;
             }
@@ -89,22 +89,29 @@ __device__ void cta_radix_select_kth(const HiT* __restrict__ hi, const uint32_t*
         if (in_bin == 1 && shift > 0) {
             // the k-th key is the only key with this prefix: fetch it instead of histogramming its remaining bytes
             for (int i = threadIdx.x; i < n; i += blockDim.x) {
-                const HiT h = hi[i];
-                const uint32_t l = lo[i];
+                const HiT h = get_hi(i);
+                const uint32_t l = get_lo(i);
                 if ((h & m_hi) == p_hi && (l & m_lo) == p_lo) {
                     bcast[3] = i;
                 }
             }
             __syncthreads();
             const int idx = bcast[3];
-            kth_hi = hi[idx];
-            kth_lo = lo[idx];
+            kth_hi = get_hi(idx);
+            kth_lo = get_lo(idx);
             __syncthreads();
             return;
         }
     }
     kth_hi = p_hi;
     kth_lo = p_lo;
+}
+
+template <typename HiT>
+__device__ void cta_radix_select_kth(const HiT* __restrict__ hi, const uint32_t* __restrict__ lo, int n, int k,
+                                     int* hist, int* bcast, HiT& kth_hi, uint32_t& kth_lo) {
+    cta_radix_select_kth_by<HiT>([hi](int i) { return hi[i]; }, [lo](int i) { return lo[i]; }, n, k, hist, bcast, kth_hi,
+                                 kth_lo);
 }
 
 template <typename HiT>

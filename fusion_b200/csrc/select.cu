@@ -52,7 +52,9 @@ void prof_end(cudaStream_t stream) {
 }
 
 constexpr int kSortThreads = 1024;
-constexpr int kSelectThreads = 512;     // cand_select: two CTAs per SM (registers and shared memory) overlap each other's barriers
+// cand_select CTA size: fp32 buffers (64 KB of keys) fit two 512-thread CTAs per SM, which overlap each other's barriers;
+// fp64 buffers (96 KB) fit one, which then wants all 1024 threads
+template <typename ST> struct SelectCfg { static constexpr int threads = sizeof(ST) == 4 ? 512 : 1024, blocks = sizeof(ST) == 4 ? 2 : 1; };
 constexpr int kSmemEntries = 8192;   // 128 KB
 constexpr int kChunk = 4096;         // chunk staged through smem by the large sort
 
@@ -147,7 +149,7 @@ __device__ __forceinline__ void hi_score(uint32_t h, float& s) { s = unord32(h);
 __device__ __forceinline__ void hi_score(uint64_t h, double& s) { s = unord64(h); }
 
 template <typename ST>
-__global__ void __launch_bounds__(kSelectThreads, 2) cand_select_kernel(CandState<ST> st, int k, ST margin, int final_out,
+__global__ void __launch_bounds__(SelectCfg<ST>::threads, SelectCfg<ST>::blocks) cand_select_kernel(CandState<ST> st, int k, ST margin, int final_out,
                                                                    long long doc_base, ST* out_scores,
                                                                    int32_t* out_ids, int32_t* out_n, int k_pow2) {
     using HiT = typename HiOf<ST>::type;
@@ -278,7 +280,7 @@ int cand_select(const CandState<ST>& st, int n_queries, int k, ST margin, bool f
         done = true;
     }
     ProfScope prof(std::is_same<ST, float>::value ? "cand_select_f32" : "cand_select_f64", stream);
-    cand_select_kernel<ST><<<n_queries, kSelectThreads, smem, stream>>>(st, k, margin, final_out ? 1 : 0,
+    cand_select_kernel<ST><<<n_queries, SelectCfg<ST>::threads, smem, stream>>>(st, k, margin, final_out ? 1 : 0,
                                                                       (long long)doc_base, out_scores, out_ids, out_n,
                                                                       k_pow2);
     FZ_LAUNCH_CHECK();

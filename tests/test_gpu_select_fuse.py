@@ -194,3 +194,25 @@ def test_metrics_oracle_random_vs_kernel():
     got = ops.rank_metrics(torch.from_numpy(ids).cuda(), None, torch.from_numpy(gp).cuda(), torch.from_numpy(gi).cuda())
     exp = om.mean_metrics(golds, [r.tolist() for r in ids])
     np.testing.assert_allclose(got.cpu().numpy(), exp, rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("method,norm", [("nsf", "z-score"), ("rrf", None), ("nsf", "none"), ("bcf", None)])
+def test_fuse_truncated_output_equals_head_of_full_fusion(method, norm):
+    """out_stride < |union| takes the radix-select + short-sort path; it must equal the head of the full sort, ties
+    (constant lists, rrf ranks shared between systems) included."""
+    from fusion_b200 import ops
+    rng = np.random.Generator(np.random.PCG64(77))
+    nq, n, pool = 9, 700, 1500
+    lists = []
+    for s in range(4):
+        ids = np.stack([rng.permutation(pool)[:n] for _ in range(nq)]).astype(np.int32)
+        sc = -np.sort(-rng.normal(0, 2, (nq, n)), axis=1)
+        if s == 2:
+            sc[:] = 0.75                                  # a constant list: every entry ties
+        lists.append((torch.from_numpy(ids).cuda(), torch.from_numpy(sc).cuda(), None))
+    w = [0.4, 0.3, 0.2, 0.1] if method == "nsf" else None
+    full_i, full_s, full_n = ops.fuse(lists, method, norm, w)
+    for stride in (1, 37, 1000):
+        ti, ts, tn = ops.fuse(lists, method, norm, w, out_stride=stride)
+        assert torch.equal(ti, full_i[:, :stride]) and torch.equal(ts, full_s[:, :stride])
+        assert torch.equal(tn, torch.clamp(full_n, max=stride))
