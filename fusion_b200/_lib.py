@@ -63,7 +63,8 @@ SIGNATURES = {
     "fz_dense_scores_f32": (_i, [_p, _p, _i, _i64, _i, _p, _p]),
     "fz_normalize_rows": (_i, [_p, _i64, _i, _i, _p, _p, _p]),
     "fz_maxsim_workspace_bytes": (_sz, [_i, _i]),
-    "fz_maxsim_bf16": (_i, [_p, _i, _p, _p, _p, _i64, _i64, _i64, _i, _i, _p, _p, _sz, _p]),
+    "fz_maxsim_pack": (_i, [_p, _p, _p, _i64, _p, _p]),
+    "fz_maxsim_bf16": (_i, [_p, _i, _p, _p, _p, _p, _i64, _i64, _i, _i, _p, _p, _sz, _p]),
 }
 
 _lib = None

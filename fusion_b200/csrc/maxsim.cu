@@ -4,15 +4,19 @@
 //   src/utils/colbert_ir.py:245-255, src/retrievers/hybrid.py:109-137)
 //
 // Layout: the UMMA A operand is the query's token matrix (rows = query tokens -> TMEM lanes), the B operand is a
-// GROUP of candidate documents' token blocks packed back to back (rows = doc tokens -> TMEM columns, up to 256 per
+// GROUP of candidate passages' token blocks packed back to back (rows = doc tokens -> TMEM columns, up to 256 per
 // MMA), K = 128 embedding dims.  The max over doc tokens is then a per-thread running max over the columns each
 // epilogue thread reads back with tcgen05.ld, and the sum over query tokens one warp reduction per candidate.
-// A persistent CTA owns whole queries: warp 0 streams the candidates' token rows with TMA (one 2-D box per 64-dim
-// half and candidate, box height = the doc length rounded up to 16, so a 70-token passage moves 80 rows) into a
-// 3-stage ring of 64 KB groups, warp 1 issues 8 MMAs per group into one of two 256-column TMEM accumulators, two
-// teams of epilogue warps reduce alternate groups.  Packing ~3 passages per group amortises the barrier round
-// trips and the shared-memory reads of the query operand.  The kernel is HBM-bound: 2*Lq = 128 FLOP per bf16
-// element read.
+//
+// The token store is kept in HBM in the exact image the UMMA wants in shared memory (fz_maxsim_pack): per passage the
+// two 64-dim halves as 128-byte rows, rows padded to a multiple of 8, 16-byte chunks pre-swizzled (chunk ^ row % 8).
+// A passage therefore arrives with two plain bulk copies of exactly its bytes - no tensor map per box height (switching
+// between them serialised the TMA unit), no rounding of the row count to the box, and the bytes of a passage are
+// contiguous in HBM.  A persistent CTA owns whole queries: warp 0 streams the passages into a 3-stage ring of 64 KB
+// groups, warp 1 issues 8 MMAs per group into one of two 256-column TMEM accumulators, two teams of epilogue warps
+// reduce alternate passages.  Packing ~3 passages per group amortises the barrier round trips, the >= 95-cycle issue
+// cost of a tcgen05.mma and the shared-memory reads of the query operand.  The kernel is HBM-bound: 2*Lq = 128 FLOP
+// per bf16 element read.
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -30,16 +34,15 @@ constexpr int kMsGroupMax = 256;            // doc-token rows per MMA group (UMM
 constexpr int kMsStages = 3;
 constexpr int kMsTBufs = 2;                 // 2 x 256 TMEM columns
 constexpr int kMsThreads = 384;             // warps 0-3 control, warps 4-7 and 8-11 two epilogue teams
-constexpr int kMsBoxes = kMsGroupMax / 16;  // tensor maps with box heights 16, 32, ..., 256
 constexpr size_t kMsSmemMax = 227 * 1024;
 
 struct alignas(64) MsMaps {
     CUtensorMap q;
-    CUtensorMap d[kMsBoxes];
 };
 
 struct MsArgs {
-    const int2* info;           // [n_queries, n_cand] (first token row, token count | -1 = not in this shard)
+    const int2* info;           // [n_queries, n_cand] (first packed row, token count | -1 = not in this shard)
+    const unsigned char* packed;   // packed token store (fz_maxsim_pack): 256 bytes per packed row
     int n_queries, n_cand, lq;
     int a_rows;                 // query rows held in shared memory per 64-dim half (lq rounded up to 8)
     int group_rows;             // doc-token rows per stage (multiple of 16, <= 256)
@@ -50,16 +53,32 @@ struct MsArgs {
 // (start row, token count) of every (query, candidate) pair, gathered once by a pre-pass: under a saturated memory
 // system a demand load takes thousands of cycles, so the persistent kernel must not chase cand -> tok_ptr -> tokens
 // pointers on its critical path.  len -1 = candidate outside this shard.
-__global__ void maxsim_info_kernel(const int32_t* __restrict__ cand, const int64_t* __restrict__ tok_ptr, long long n_docs,
-                                   long long doc_base, long long n_pairs, int2* __restrict__ info) {
+__global__ void maxsim_info_kernel(const int32_t* __restrict__ cand, const int64_t* __restrict__ tok_ptr,
+                                   const int64_t* __restrict__ pk_ptr, long long n_docs, long long doc_base,
+                                   long long n_pairs, int2* __restrict__ info) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_pairs; i += (long long)gridDim.x * blockDim.x) {
         const long long d = (long long)cand[i] - doc_base;
         int2 v = make_int2(0, -1);
-        if (d >= 0 && d < n_docs) {
-            const long long s = tok_ptr[d], e = tok_ptr[d + 1];
-            v = make_int2((int)s, (int)(e - s));
-        }
+        if (d >= 0 && d < n_docs) v = make_int2((int)pk_ptr[d], (int)(tok_ptr[d + 1] - tok_ptr[d]));
         info[i] = v;
+    }
+}
+
+// Packed image of one passage: [half 0: R rows x 128 B][half 1: R rows x 128 B], R = rows rounded up to 8 (zero rows),
+// the 16-byte chunk c of row r stored at chunk c ^ (r % 8) - the 128-byte swizzle of the UMMA K-major layout.
+__global__ void maxsim_pack_kernel(const int64_t* __restrict__ tok_ptr, const uint4* __restrict__ emb,
+                                   const int64_t* __restrict__ pk_ptr, long long n_docs, uint4* __restrict__ packed) {
+    for (long long d = blockIdx.x; d < n_docs; d += gridDim.x) {
+        const long long t0 = tok_ptr[d];
+        const int len = (int)(tok_ptr[d + 1] - t0);
+        const long long p0 = pk_ptr[d];
+        const int R = (int)(pk_ptr[d + 1] - p0);
+        uint4* dst = packed + (size_t)p0 * 16;                  // 16 uint4 per packed row (256 B)
+        for (int i = threadIdx.x; i < R * 16; i += blockDim.x) {
+            const int r = i >> 4, c = i & 15, half = c >> 3, cc = c & 7;
+            const uint4 v = r < len ? emb[(size_t)(t0 + r) * 16 + c] : make_uint4(0, 0, 0, 0);
+            dst[(size_t)half * R * 8 + (size_t)r * 8 + (cc ^ (r & 7))] = v;
+        }
     }
 }
 
@@ -71,8 +90,10 @@ __device__ __forceinline__ int2 ms_cand_info(const MsArgs& M, int q, int c0, int
 // Walk query q's candidates and cut them into pieces (<= group_rows tokens) packed greedily into groups.  Every role
 // (producer, MMA issuer, both epilogue teams) runs this same warp-uniform walk, so they agree on the packing without
 // exchanging anything.
-//   on_piece(c, start_row, n, R, col, first_of_cand, last_of_cand, first_of_group)
-//   on_group_end(rows)           rows = columns of the group (multiple of 16)
+//   on_piece(c, row0, off, Rdoc, n, R, col, first_of_cand, last_of_cand, first_of_group)
+//                                row0 = first packed row of the passage, off = first token of the piece, Rdoc / R =
+//                                rows of the passage / piece rounded up to 8, col = first TMEM column of the piece
+//   on_group_end(rows)           rows = columns of the group (multiple of 8; the MMA rounds up to 16)
 //   on_empty(c)                  candidate with zero tokens
 template <class FP, class FG, class FE>
 __device__ __forceinline__ void ms_walk(const MsArgs& M, int q, int lane, FP on_piece, FG on_group_end, FE on_empty) {
@@ -90,14 +111,18 @@ __device__ __forceinline__ void ms_walk(const MsArgs& M, int q, int lane, FP on_
                 if (len == 0) on_empty(c0 + l);
                 continue;
             }
-            for (int off = 0; off < len; off += M.group_rows) {
-                const int n = min(M.group_rows, len - off);
-                const int R = (n + 15) & ~15;
-                if (rows + R > M.group_rows) {
+            // 8 columns stay free at the end of a group: the epilogue's 16 / 32-column tcgen05.ld may read up to 8
+            // columns past a piece
+            const int cap = M.group_rows - 8;
+            const int Rdoc = (len + 7) & ~7;
+            for (int off = 0; off < len; off += cap) {
+                const int n = min(cap, len - off);
+                const int R = (n + 7) & ~7;
+                if (rows + R > cap) {
                     on_group_end(rows);
                     rows = 0;
                 }
-                on_piece(c0 + l, start + off, n, R, rows, off == 0, off + n >= len, rows == 0);
+                on_piece(c0 + l, start, off, Rdoc, n, R, rows, off == 0, off + n >= len, rows == 0);
                 rows += R;
             }
         }
@@ -128,7 +153,6 @@ __global__ void __launch_bounds__(kMsThreads, 1) maxsim_kernel(const __grid_cons
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&maps.q);
-        for (int i = 0; i < kMsBoxes; ++i) ptx::prefetch_tensormap(&maps.d[i]);
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < kMsStages; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 1); }
@@ -163,7 +187,7 @@ __global__ void __launch_bounds__(kMsThreads, 1) maxsim_kernel(const __grid_cons
             }
             __syncwarp();
             ms_walk(M, q, lane,
-                [&](int, int row0, int, int R, int col, bool, bool, bool first_of_group) {
+                [&](int, int row0, int off, int Rdoc, int, int R, int col, bool, bool, bool first_of_group) {
                     if (lane == 0) {
                         if (first_of_group) {
                             const long long t0 = FZ_CLOCK();
@@ -171,10 +195,10 @@ __global__ void __launch_bounds__(kMsThreads, 1) maxsim_kernel(const __grid_cons
                             st_wait_empty += FZ_CLOCK() - t0;
                         }
                         unsigned char* sb = smem_b + (size_t)stage * b_bytes + (size_t)col * 128;
-                        const CUtensorMap* mp = &maps.d[R / 16 - 1];
-                        ptx::mbar_expect_tx(&full_bar[stage], (uint32_t)R * kMsDim * 2);
-                        ptx::tma_load_2d(sb, mp, &full_bar[stage], 0, row0);
-                        ptx::tma_load_2d(sb + b_half, mp, &full_bar[stage], 64, row0);
+                        const unsigned char* src = M.packed + (size_t)row0 * 256 + (size_t)off * 128;
+                        ptx::mbar_expect_tx(&full_bar[stage], (uint32_t)R * 256);
+                        ptx::bulk_load(sb, src, (uint32_t)R * 128, &full_bar[stage]);                               // dims 0..63
+                        ptx::bulk_load(sb + b_half, src + (size_t)Rdoc * 128, (uint32_t)R * 128, &full_bar[stage]);   // 64..127
                     }
                     __syncwarp();
                 },
@@ -202,7 +226,7 @@ __global__ void __launch_bounds__(kMsThreads, 1) maxsim_kernel(const __grid_cons
             __syncwarp();
             const uint32_t sa = ptx::smem_u32(smem_a + (size_t)abuf * a_bytes);
             ms_walk(M, q, lane,
-                [&](int, int, int, int, int, bool, bool, bool) {},
+                [&](int, int, int, int, int, int, int, bool, bool, bool) {},
                 [&](int rows) {
                     if (lane == 0) {
                         const uint32_t tb = g % kMsTBufs;
@@ -215,7 +239,7 @@ __global__ void __launch_bounds__(kMsThreads, 1) maxsim_kernel(const __grid_cons
                         st_wait_full += t2 - t1;
                         ptx::tc_fence_after();
                         const uint32_t sb = ptx::smem_u32(smem_b + (size_t)stage * b_bytes);
-                        const uint32_t idesc = ptx::make_idesc_bf16(kMsRows, (uint32_t)rows);
+                        const uint32_t idesc = ptx::make_idesc_bf16(kMsRows, (uint32_t)((rows + 15) & ~15));
                         const uint32_t d_tmem = tmem_base + tb * kMsGroupMax;
 #pragma unroll
                         for (int k = 0; k < kMsDim / 16; ++k) {
@@ -257,7 +281,7 @@ __global__ void __launch_bounds__(kMsThreads, 1) maxsim_kernel(const __grid_cons
             const long long st_begin = FZ_CLOCK();
             for (int q = blockIdx.x; q < M.n_queries; q += gridDim.x) {
                 ms_walk(M, q, lane,
-                    [&](int c, int, int n, int, int col, bool first_of_cand, bool last_of_cand, bool first_of_group) {
+                    [&](int c, int, int, int, int n, int, int col, bool first_of_cand, bool last_of_cand, bool first_of_group) {
                         const uint32_t tb = g % kMsTBufs;
                         if (first_of_group) {
                             const long long t0 = FZ_CLOCK();
@@ -357,14 +381,24 @@ extern "C" size_t fz_maxsim_workspace_bytes(int n_queries, int n_cand) {
     return (size_t)n_queries * (size_t)n_cand * sizeof(int2);
 }
 
+extern "C" int fz_maxsim_pack(const int64_t* tok_ptr, const void* tok_emb, const int64_t* pk_ptr, int64_t n_docs,
+                              void* packed, fz_stream_t stream) {
+    FZ_REQUIRE(tok_ptr && tok_emb && pk_ptr && packed && n_docs >= 1, "bad arguments");
+    FZ_REQUIRE((((uintptr_t)tok_emb | (uintptr_t)packed) & 15) == 0, "token store must be 16-byte aligned");
+    const int blocks = (int)(n_docs < 148 * 64 ? n_docs : 148 * 64);
+    maxsim_pack_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(tok_ptr, (const uint4*)tok_emb, pk_ptr, n_docs, (uint4*)packed);
+    FZ_LAUNCH_CHECK();
+    return FZ_OK;
+}
+
 extern "C" int fz_maxsim_bf16(const void* q_tok, int lq, const int32_t* cand_ids, const int64_t* tok_ptr,
-                              const void* tok_emb, int64_t n_tokens, int64_t n_docs, int64_t doc_base, int n_queries,
+                              const int64_t* pk_ptr, const void* packed, int64_t n_docs, int64_t doc_base, int n_queries,
                               int n_cand, float* out_scores, void* ws, size_t ws_bytes, fz_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    FZ_REQUIRE(q_tok && cand_ids && tok_ptr && tok_emb && out_scores, "null pointer");
+    FZ_REQUIRE(q_tok && cand_ids && tok_ptr && pk_ptr && packed && out_scores, "null pointer");
+    FZ_REQUIRE(((uintptr_t)packed & 1023) == 0, "the packed token store must be 1024-byte aligned");
     FZ_REQUIRE(ws && ws_bytes >= fz_maxsim_workspace_bytes(n_queries, n_cand) && ((uintptr_t)ws & 7) == 0, "workspace too small");
     FZ_REQUIRE(lq >= 1 && lq <= kMsRows, "lq=%d must be in [1,%d]", lq, kMsRows);
-    FZ_REQUIRE(n_tokens >= 1 && n_tokens < (1ll << 31), "n_tokens out of range");
     FZ_REQUIRE(n_docs >= 1 && n_cand >= 1, "bad sizes");
     if (n_queries == 0) return FZ_OK;
     FZ_REQUIRE((long long)n_queries * lq < (1ll << 31), "too many query tokens");
@@ -373,11 +407,12 @@ extern "C" int fz_maxsim_bf16(const void* q_tok, int lq, const int32_t* cand_ids
         const long long n_pairs = (long long)n_queries * n_cand;
         const int blocks = (int)(ceil_div<long long>(n_pairs, 256) < 148 * 16 ? ceil_div<long long>(n_pairs, 256) : 148 * 16);
         ProfScope prof("maxsim_info", stream);
-        maxsim_info_kernel<<<blocks, 256, 0, stream>>>(cand_ids, tok_ptr, n_docs, doc_base, n_pairs, (int2*)ws);
+        maxsim_info_kernel<<<blocks, 256, 0, stream>>>(cand_ids, tok_ptr, pk_ptr, n_docs, doc_base, n_pairs, (int2*)ws);
         FZ_LAUNCH_CHECK();
     }
     MsArgs M;
     M.info = (const int2*)ws;
+    M.packed = (const unsigned char*)packed;
     M.n_queries = n_queries;
     M.n_cand = n_cand;
     M.lq = lq;
@@ -397,10 +432,6 @@ extern "C" int fz_maxsim_bf16(const void* q_tok, int lq, const int32_t* cand_ids
     MsMaps maps;
     int rc = make_bf16_tile_map(&maps.q, q_tok, (uint64_t)n_queries * lq, kMsDim, (uint32_t)M.a_rows);
     if (rc) return rc;
-    for (int i = 0; i < kMsBoxes; ++i) {
-        rc = make_bf16_tile_map(&maps.d[i], tok_emb, (uint64_t)n_tokens, kMsDim, 16 * (i + 1));
-        if (rc) return rc;
-    }
     static bool attr = false;
     if (!attr) {
         FZ_CUDA(cudaFuncSetAttribute(maxsim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMsSmemMax));

@@ -85,6 +85,13 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
         : "memory");
 }
 
+// plain bulk copy global -> shared (no tensor map): `bytes` (multiple of 16) from a 16-byte aligned address
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :
+                 : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gmem_src)), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
 // same, multicast: the box lands at the same CTA-relative offset in every CTA of `cta_mask` and each of those CTAs'
 // mbarrier (same offset) receives the complete_tx
 __device__ __forceinline__ void tma_load_2d_multicast(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int32_t c0,

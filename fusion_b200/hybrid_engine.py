@@ -116,7 +116,8 @@ class HybridSearcher:
         cand = lists[src][1]                                            # [Qs, k] global ids of this rank's query slice
         cand_all = sharding.allgather_rows(cand, self.group)[: q.colbert.shape[0]] if self.world > 1 else cand
         pool_ids = cand_all if self.colbert_pool is None else torch.where(cand_all >= 0, cand_all % self.colbert_pool, cand_all)
-        part = ops.maxsim(q.colbert, self.tokens.tok_ptr, self.tokens.tok_emb, pool_ids.contiguous(), self.tokens.doc_base)
+        part = ops.maxsim(q.colbert, self.tokens.tok_ptr, None, pool_ids.contiguous(), self.tokens.doc_base,
+                          packed=self.tokens.packed())
         sc = sharding.reduce_scatter_scores(part, self.group) if self.world > 1 else part
         sc = torch.where(cand >= 0, sc[: cand.shape[0]], torch.full_like(sc[: cand.shape[0]], float("-inf")))
         order_s, order_i = ops.rank_rows(sc.contiguous(), cand.shape[1], 0)

@@ -307,11 +307,24 @@ class DenseIndex:
 
 @dataclass
 class TokenStore:
-    """ColBERT token embeddings of one corpus shard (rows of doc d are tok_ptr[d]:tok_ptr[d+1])."""
-    tok_ptr: torch.Tensor    # int64 [N+1]
-    tok_emb: torch.Tensor    # bf16 [T, 128]
+    """ColBERT token embeddings of one corpus shard (rows of doc d are tok_ptr[d]:tok_ptr[d+1]).  The MaxSim kernel
+    streams the PACKED image (ops.pack_tokens), built on first use; ``drop_plain`` then frees the [T, 128] matrix."""
+    tok_ptr: torch.Tensor            # int64 [N+1]
+    tok_emb: torch.Tensor | None     # bf16 [T, 128]
     doc_base: int = 0
+    _packed: tuple | None = None
 
     @property
     def n_docs(self) -> int:
         return self.tok_ptr.numel() - 1
+
+    @property
+    def n_tokens(self) -> int:
+        return int(self.tok_ptr[-1])
+
+    def packed(self, drop_plain: bool = False):
+        if self._packed is None:
+            self._packed = ops.pack_tokens(self.tok_ptr, self.tok_emb)
+        if drop_plain:
+            self.tok_emb = None
+        return self._packed

@@ -433,22 +433,49 @@ def dense_scores(q_f32, d_f32):
 
 
 # ----------------------------------------------------------------------------------------------- K3
-def maxsim(q_tok_bf16, tok_ptr, tok_emb_bf16, cand_ids, doc_base: int = 0):
+def pack_tokens(tok_ptr: torch.Tensor, tok_emb_bf16: torch.Tensor):
+    """Token store -> the packed image the MaxSim kernel streams (per passage two 64-dim halves of 128-byte rows, rows
+    padded to 8, 16-byte chunks pre-swizzled for the UMMA layout).  -> (pk_ptr int64 [N+1] packed-row offsets, packed uint8)."""
+    lib = _lib.load()
+    tok_ptr = _req(tok_ptr, torch.int64, "tok_ptr")
+    tok_emb_bf16 = _req(tok_emb_bf16, torch.bfloat16, "tok_emb")
+    if tok_emb_bf16.shape[1] != 128:
+        raise FusionB200Error("maxsim needs 128-dimensional token embeddings")
+    lens = tok_ptr[1:] - tok_ptr[:-1]
+    pk_ptr = torch.zeros_like(tok_ptr)
+    pk_ptr[1:] = torch.cumsum((lens + 7) // 8 * 8, 0)
+    total = int(pk_ptr[-1])
+    if total >= (1 << 31):
+        raise FusionB200Error("token store too large for one shard (2^31 packed rows)")
+    packed = torch.empty(max(total, 8) * 256 + 1024, dtype=torch.uint8, device=tok_emb_bf16.device)
+    shift = (-packed.data_ptr()) % 1024
+    packed = packed[shift: shift + max(total, 8) * 256]                     # 1024-byte aligned view
+    n_docs = tok_ptr.numel() - 1
+    if n_docs:
+        check(lib.fz_maxsim_pack(_ptr(tok_ptr), _ptr(tok_emb_bf16), _ptr(pk_ptr), n_docs, _ptr(packed), _stream(packed)),
+              "fz_maxsim_pack")
+    return pk_ptr, packed
+
+
+def maxsim(q_tok_bf16, tok_ptr, tok_emb_bf16, cand_ids, doc_base: int = 0, packed=None):
     """ColBERT MaxSim of every (query, candidate) pair -> fp32 [Q, C].
 
-    q_tok_bf16 [Q, Lq, 128], tok_ptr int64 [N+1], tok_emb_bf16 [T, 128], cand_ids int32 [Q, C] (global ids;
-    candidates outside [doc_base, doc_base+N) are skipped and score 0)."""
+    q_tok_bf16 [Q, Lq, 128], tok_ptr int64 [N+1], cand_ids int32 [Q, C] (global ids; candidates outside
+    [doc_base, doc_base+N) are skipped and score 0).  ``packed`` = ``pack_tokens(tok_ptr, tok_emb)`` (TokenStore keeps
+    it); without it the plain ``tok_emb_bf16`` [T, 128] is packed on the fly."""
     lib = _lib.load()
     q_tok_bf16 = _req(q_tok_bf16, torch.bfloat16, "q_tok")
-    tok_emb_bf16 = _req(tok_emb_bf16, torch.bfloat16, "tok_emb")
     tok_ptr = _req(tok_ptr, torch.int64, "tok_ptr")
     cand_ids = _req(cand_ids, torch.int32, "cand_ids")
     nq, lq, dim = q_tok_bf16.shape
-    if dim != 128 or tok_emb_bf16.shape[1] != 128:
+    if dim != 128:
         raise FusionB200Error("maxsim needs 128-dimensional token embeddings")
+    if packed is None:
+        packed = pack_tokens(tok_ptr, tok_emb_bf16)
+    pk_ptr, pk = packed
     out = torch.empty(cand_ids.shape, dtype=torch.float32, device=cand_ids.device)
     ws = _ws(lib.fz_maxsim_workspace_bytes(nq, cand_ids.shape[1]), cand_ids.device)
-    check(lib.fz_maxsim_bf16(_ptr(q_tok_bf16), lq, _ptr(cand_ids), _ptr(tok_ptr), _ptr(tok_emb_bf16),
-                             tok_emb_bf16.shape[0], tok_ptr.numel() - 1, doc_base, nq, cand_ids.shape[1], _ptr(out),
-                             _ptr(ws), ws.numel(), _stream(out)), "fz_maxsim_bf16")
+    check(lib.fz_maxsim_bf16(_ptr(q_tok_bf16), lq, _ptr(cand_ids), _ptr(tok_ptr), _ptr(pk_ptr), _ptr(pk),
+                             tok_ptr.numel() - 1, doc_base, nq, cand_ids.shape[1], _ptr(out), _ptr(ws), ws.numel(),
+                             _stream(out)), "fz_maxsim_bf16")
     return out

@@ -171,7 +171,7 @@ class Ranker:
         nq = q16.shape[0]
         if cand_ids is None:
             cand_ids = (torch.arange(store.n_docs, dtype=torch.int32, device=q16.device) + store.doc_base).expand(nq, -1).contiguous()
-        sc = ops.maxsim(q16, store.tok_ptr, store.tok_emb, cand_ids, store.doc_base)
+        sc = ops.maxsim(q16, store.tok_ptr, None, cand_ids, store.doc_base, packed=store.packed())
         k = min(top_k, cand_ids.shape[1])
         order_s, order_i = ops.rank_rows(sc, k, 0)
         return order_s, torch.gather(cand_ids, 1, order_i.long())

@@ -234,14 +234,21 @@ int fz_normalize_rows(const float* x, int64_t n_rows, int dim, int normalize, fl
  * K3  ColBERT MaxSim over candidate token tiles: S(q, d) = sum_i max_j <Q_i, D_j>  (tcgen05, bf16 in, fp32 acc).
  * Replaces colbert-ai `colbert_score` reached through CustomSearcher.search_all (src/utils/colbert_ir.py:245-255)
  * and Ranker.multi_vector_search (src/retrievers/hybrid.py:109-137).
- *   q_tok [n_queries * lq, 128] bf16, tok_ptr [n_docs + 1] int64, tok_emb [n_tokens, 128] bf16,
- *   cand_ids [n_queries, n_cand] global ids (ids outside [doc_base, doc_base + n_docs) are skipped, score 0)
- *   out_scores [n_queries, n_cand] fp32
- *   ws: fz_maxsim_workspace_bytes(...) of scratch (the gathered (first token row, length) of every pair)
+ *
+ * The token store is kept PACKED: per passage the two 64-dim halves as 128-byte rows, rows padded to a multiple of 8,
+ * 16-byte chunks pre-swizzled for the UMMA shared-memory layout, so a passage is fetched with two plain bulk copies.
+ *   fz_maxsim_pack: tok_ptr [n_docs + 1] int64 token offsets, tok_emb [n_tokens, 128] bf16 (16-byte aligned),
+ *                   pk_ptr [n_docs + 1] int64 packed-row offsets (pk_ptr[d+1] - pk_ptr[d] = tokens of d rounded up to 8),
+ *                   packed [pk_ptr[n_docs] * 256 bytes], 1024-byte aligned.
+ *   fz_maxsim_bf16: q_tok [n_queries * lq, 128] bf16, cand_ids [n_queries, n_cand] global ids (ids outside
+ *                   [doc_base, doc_base + n_docs) are skipped, score 0), out_scores [n_queries, n_cand] fp32,
+ *                   ws: fz_maxsim_workspace_bytes(...) of scratch (gathered (first packed row, length) of every pair).
  * ---------------------------------------------------------------------------------------------------------- */
 size_t fz_maxsim_workspace_bytes(int n_queries, int n_cand);
-int fz_maxsim_bf16(const void* q_tok, int lq, const int32_t* cand_ids, const int64_t* tok_ptr, const void* tok_emb,
-                   int64_t n_tokens, int64_t n_docs, int64_t doc_base, int n_queries, int n_cand, float* out_scores,
+int fz_maxsim_pack(const int64_t* tok_ptr, const void* tok_emb, const int64_t* pk_ptr, int64_t n_docs, void* packed,
+                   fz_stream_t stream);
+int fz_maxsim_bf16(const void* q_tok, int lq, const int32_t* cand_ids, const int64_t* tok_ptr, const int64_t* pk_ptr,
+                   const void* packed, int64_t n_docs, int64_t doc_base, int n_queries, int n_cand, float* out_scores,
                    void* ws, size_t ws_bytes, fz_stream_t stream);
 
 #ifdef __cplusplus

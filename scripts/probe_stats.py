@@ -17,11 +17,12 @@ if which == "maxsim":
     emb = (emb / emb.norm(dim=1, keepdim=True)).bfloat16()
     q = torch.randn((nq, 64, 128), device=dev, generator=g); q = (q / q.norm(dim=2, keepdim=True)).bfloat16()
     cand = torch.randint(0, pool, (nq, nc), device=dev, generator=g, dtype=torch.int32)
+    packed = ops.pack_tokens(ptr, emb)
     for it in range(3):
         stats.zero_()
         lib.fz_debug_set_stats(ctypes.c_void_p(stats.data_ptr()))
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(); ops.maxsim(q, ptr, emb, cand); b.record(); torch.cuda.synchronize()
+        a.record(); ops.maxsim(q, ptr, None, cand, packed=packed); b.record(); torch.cuda.synchronize()
         lib.fz_debug_set_stats(ctypes.c_void_p(0))
     ms = a.elapsed_time(b)
     units = nq * nc / 148
