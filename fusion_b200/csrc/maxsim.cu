@@ -41,7 +41,8 @@ struct alignas(64) MsMaps {
 };
 
 struct MsArgs {
-    const int2* info;           // [n_queries, n_cand] (first packed row, token count | -1 = not in this shard)
+    const int4* info;           // [n_queries, n_cand] owned candidates: (first packed row, token count, candidate, 0)
+    const int32_t* count;       // [n_queries] how many of them
     const unsigned char* packed;   // packed token store (fz_maxsim_pack): 256 bytes per packed row
     int n_queries, n_cand, lq;
     int a_rows;                 // query rows held in shared memory per 64-dim half (lq rounded up to 8)
@@ -53,15 +54,27 @@ struct MsArgs {
 // (start row, token count) of every (query, candidate) pair, gathered once by a pre-pass: under a saturated memory
 // system a demand load takes thousands of cycles, so the persistent kernel must not chase cand -> tok_ptr -> tokens
 // pointers on its critical path.  len -1 = candidate outside this shard.
+// One warp per query: the candidates this shard owns, compacted in candidate order, as (first packed row, token count,
+// candidate index, 0).  A shard of a G-way sharded store owns 1/G of them: the persistent kernel walks only those.
 __global__ void maxsim_info_kernel(const int32_t* __restrict__ cand, const int64_t* __restrict__ tok_ptr,
-                                   const int64_t* __restrict__ pk_ptr, long long n_docs, long long doc_base,
-                                   long long n_pairs, int2* __restrict__ info) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_pairs; i += (long long)gridDim.x * blockDim.x) {
-        const long long d = (long long)cand[i] - doc_base;
-        int2 v = make_int2(0, -1);
-        if (d >= 0 && d < n_docs) v = make_int2((int)pk_ptr[d], (int)(tok_ptr[d + 1] - tok_ptr[d]));
-        info[i] = v;
+                                   const int64_t* __restrict__ pk_ptr, long long n_docs, long long doc_base, int n_queries,
+                                   int n_cand, int4* __restrict__ info, int32_t* __restrict__ count) {
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= n_queries) return;
+    int n_own = 0;
+    for (int c0 = 0; c0 < n_cand; c0 += 32) {
+        const int c = c0 + lane;
+        int4 v = make_int4(0, -1, c, 0);
+        if (c < n_cand) {
+            const long long d = (long long)cand[(size_t)q * n_cand + c] - doc_base;
+            if (d >= 0 && d < n_docs) v = make_int4((int)pk_ptr[d], (int)(tok_ptr[d + 1] - tok_ptr[d]), c, 0);
+        }
+        const unsigned own = __ballot_sync(0xffffffffu, v.y >= 0);
+        if (v.y >= 0) info[(size_t)q * n_cand + n_own + __popc(own & ((1u << lane) - 1))] = v;
+        n_own += __popc(own);
     }
+    if (lane == 0) count[q] = n_own;
 }
 
 // Packed image of one passage: [half 0: R rows x 128 B][half 1: R rows x 128 B], R = rows rounded up to 8 (zero rows),
@@ -82,9 +95,9 @@ __global__ void maxsim_pack_kernel(const int64_t* __restrict__ tok_ptr, const ui
     }
 }
 
-__device__ __forceinline__ int2 ms_cand_info(const MsArgs& M, int q, int c0, int lane) {
+__device__ __forceinline__ int4 ms_cand_info(const MsArgs& M, int q, int c0, int lane, int n_own) {
     const int c = c0 + lane;
-    return c < M.n_cand ? __ldg(&M.info[(size_t)q * M.n_cand + c]) : make_int2(0, -1);
+    return c < n_own ? __ldg(&M.info[(size_t)q * M.n_cand + c]) : make_int4(0, -1, 0, 0);
 }
 
 // Walk query q's candidates and cut them into pieces (<= group_rows tokens) packed greedily into groups.  Every role
@@ -98,17 +111,19 @@ __device__ __forceinline__ int2 ms_cand_info(const MsArgs& M, int q, int c0, int
 template <class FP, class FG, class FE>
 __device__ __forceinline__ void ms_walk(const MsArgs& M, int q, int lane, FP on_piece, FG on_group_end, FE on_empty) {
     int rows = 0;
-    int2 i1 = ms_cand_info(M, q, 0, lane), i2 = ms_cand_info(M, q, 32, lane);   // two blocks of 32 in flight
-    for (int c0 = 0; c0 < M.n_cand; c0 += 32) {
-        const int2 cur = i1;
+    const int n_own = __ldg(&M.count[q]);
+    int4 i1 = ms_cand_info(M, q, 0, lane, n_own), i2 = ms_cand_info(M, q, 32, lane, n_own);   // two blocks of 32 in flight
+    for (int c0 = 0; c0 < n_own; c0 += 32) {
+        const int4 cur = i1;
         i1 = i2;
-        i2 = ms_cand_info(M, q, c0 + 64, lane);
-        const int nb = min(32, M.n_cand - c0);
+        i2 = ms_cand_info(M, q, c0 + 64, lane, n_own);
+        const int nb = min(32, n_own - c0);
         for (int l = 0; l < nb; ++l) {
             const int start = __shfl_sync(0xffffffffu, cur.x, l);
             const int len = __shfl_sync(0xffffffffu, cur.y, l);
+            const int cidx = __shfl_sync(0xffffffffu, cur.z, l);
             if (len <= 0) {
-                if (len == 0) on_empty(c0 + l);
+                if (len == 0) on_empty(cidx);
                 continue;
             }
             // 8 columns stay free at the end of a group: the epilogue's 16 / 32-column tcgen05.ld may read up to 8
@@ -122,7 +137,7 @@ __device__ __forceinline__ void ms_walk(const MsArgs& M, int q, int lane, FP on_
                     on_group_end(rows);
                     rows = 0;
                 }
-                on_piece(c0 + l, start, off, Rdoc, n, R, rows, off == 0, off + n >= len, rows == 0);
+                on_piece(cidx, start, off, Rdoc, n, R, rows, off == 0, off + n >= len, rows == 0);
                 rows += R;
             }
         }
@@ -378,7 +393,7 @@ extern "C" int fz_debug_set_stats(void* device_buffer) {
 }
 
 extern "C" size_t fz_maxsim_workspace_bytes(int n_queries, int n_cand) {
-    return (size_t)n_queries * (size_t)n_cand * sizeof(int2);
+    return (size_t)n_queries * (size_t)n_cand * sizeof(int4) + align_up((size_t)n_queries * sizeof(int32_t), 16);
 }
 
 extern "C" int fz_maxsim_pack(const int64_t* tok_ptr, const void* tok_emb, const int64_t* pk_ptr, int64_t n_docs,
@@ -397,21 +412,23 @@ extern "C" int fz_maxsim_bf16(const void* q_tok, int lq, const int32_t* cand_ids
     cudaStream_t stream = (cudaStream_t)stream_;
     FZ_REQUIRE(q_tok && cand_ids && tok_ptr && pk_ptr && packed && out_scores, "null pointer");
     FZ_REQUIRE(((uintptr_t)packed & 1023) == 0, "the packed token store must be 1024-byte aligned");
-    FZ_REQUIRE(ws && ws_bytes >= fz_maxsim_workspace_bytes(n_queries, n_cand) && ((uintptr_t)ws & 7) == 0, "workspace too small");
+    FZ_REQUIRE(ws && ws_bytes >= fz_maxsim_workspace_bytes(n_queries, n_cand) && ((uintptr_t)ws & 15) == 0, "workspace too small");
     FZ_REQUIRE(lq >= 1 && lq <= kMsRows, "lq=%d must be in [1,%d]", lq, kMsRows);
     FZ_REQUIRE(n_docs >= 1 && n_cand >= 1, "bad sizes");
     if (n_queries == 0) return FZ_OK;
     FZ_REQUIRE((long long)n_queries * lq < (1ll << 31), "too many query tokens");
 
+    int4* info = (int4*)ws;
+    int32_t* count = (int32_t*)((char*)ws + (size_t)n_queries * n_cand * sizeof(int4));
     {
-        const long long n_pairs = (long long)n_queries * n_cand;
-        const int blocks = (int)(ceil_div<long long>(n_pairs, 256) < 148 * 16 ? ceil_div<long long>(n_pairs, 256) : 148 * 16);
         ProfScope prof("maxsim_info", stream);
-        maxsim_info_kernel<<<blocks, 256, 0, stream>>>(cand_ids, tok_ptr, pk_ptr, n_docs, doc_base, n_pairs, (int2*)ws);
+        maxsim_info_kernel<<<ceil_div(n_queries, 8), 256, 0, stream>>>(cand_ids, tok_ptr, pk_ptr, n_docs, doc_base, n_queries,
+                                                                       n_cand, info, count);
         FZ_LAUNCH_CHECK();
     }
     MsArgs M;
-    M.info = (const int2*)ws;
+    M.info = info;
+    M.count = count;
     M.packed = (const unsigned char*)packed;
     M.n_queries = n_queries;
     M.n_cand = n_cand;

@@ -323,6 +323,50 @@ __global__ void __launch_bounds__(kSortThreads)
         a[i] = e;
     }
     __syncthreads();
+    if (in_smem && k_out * 4 <= n && k_out <= 2048) {
+        // Only the best k_out of n are wanted (k-way merge of G top-k lists): radix-select them, then sort just those.
+        __shared__ int s_hist[256];
+        __shared__ int s_bc[4];
+        __shared__ int s_nwin;
+        __shared__ Entry s_win[2048];
+        uint64_t kth_hi = 0;
+        uint32_t kth_lo = 0;
+        // padding / invalid records carry key (0, 0): they are unique only through `payload`, so rank them by position
+        for (int i = threadIdx.x; i < n_pow2; i += blockDim.x)
+            if (a[i].payload == 0xffffffffu) a[i].tie = ~(uint32_t)(0x7f000000u + i);
+        __syncthreads();
+        const Entry* src = a;
+        const int kk = min(k_out, n);
+        cta_radix_select_kth_by<uint64_t>([src](int i) { return src[i].skey; }, [src](int i) { return src[i].tie; }, n, kk, s_hist,
+                                          s_bc, kth_hi, kth_lo);
+        if (threadIdx.x == 0) s_nwin = 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const Entry e = a[i];
+            if (key_ge<uint64_t>(e.skey, e.tie, kth_hi, kth_lo)) {
+                const int p = atomicAdd(&s_nwin, 1);
+                if (p < 2048) s_win[p] = e;
+            }
+        }
+        __syncthreads();
+        const int m = min(s_nwin, 2048);
+        int m2 = 1;
+        while (m2 < m) m2 <<= 1;
+        for (int i = m + threadIdx.x; i < m2; i += blockDim.x) s_win[i] = pad_entry();
+        __syncthreads();
+        bitonic_sort_cta(s_win, m2);
+        for (int i = threadIdx.x; i < k_out; i += blockDim.x) {
+            ST s = -std::numeric_limits<ST>::infinity();
+            int32_t d = -1;
+            if (i < m && s_win[i].payload != 0xffffffffu) {
+                key_score(s_win[i].skey, s);
+                d = (int32_t)(id_base + (long long)s_win[i].payload);
+            }
+            out_scores[(size_t)q * k_out + i] = s;
+            out_ids[(size_t)q * k_out + i] = d;
+        }
+        return;
+    }
     if (in_smem)
         bitonic_sort_cta(a, n_pow2);
     else

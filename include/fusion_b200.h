@@ -242,7 +242,7 @@ int fz_normalize_rows(const float* x, int64_t n_rows, int dim, int normalize, fl
  *                   packed [pk_ptr[n_docs] * 256 bytes], 1024-byte aligned.
  *   fz_maxsim_bf16: q_tok [n_queries * lq, 128] bf16, cand_ids [n_queries, n_cand] global ids (ids outside
  *                   [doc_base, doc_base + n_docs) are skipped, score 0), out_scores [n_queries, n_cand] fp32,
- *                   ws: fz_maxsim_workspace_bytes(...) of scratch (gathered (first packed row, length) of every pair).
+ *                   ws: fz_maxsim_workspace_bytes(...) of scratch, 16-byte aligned (the candidates this shard owns, per query).
  * ---------------------------------------------------------------------------------------------------------- */
 size_t fz_maxsim_workspace_bytes(int n_queries, int n_cand);
 int fz_maxsim_pack(const int64_t* tok_ptr, const void* tok_emb, const int64_t* pk_ptr, int64_t n_docs, void* packed,
