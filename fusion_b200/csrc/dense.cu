@@ -306,7 +306,8 @@ dense_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 // One warp per (query, kept candidate): exact fp32 dot product from the fp32 originals, in place.
 constexpr int kRescoreWarps = 8;
 __global__ void __launch_bounds__(kRescoreWarps * 32)
-rescore_kernel(const float* __restrict__ qf, const float* __restrict__ df, int dim, CandState<float> st) {
+rescore_kernel(const float* __restrict__ qf, const float* __restrict__ df, int dim, CandState<float> st,
+               const float* __restrict__ tau_floor) {
     extern __shared__ __align__(16) float qs[];
     const int q = blockIdx.x;
     for (int i = threadIdx.x; i < dim; i += blockDim.x) qs[i] = qf[(size_t)q * dim + i];
@@ -314,7 +315,14 @@ rescore_kernel(const float* __restrict__ qf, const float* __restrict__ df, int d
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n = min(st.cnt[q], st.cap);
     const size_t off = (size_t)q * st.cap;
+    // corpus-sharded runs: a candidate below the best shard's threshold cannot be in the global top-k - no need to
+    // fetch its 3 KB row
+    const float floor_q = tau_floor ? tau_floor[q] : -std::numeric_limits<float>::infinity();
     for (int i = warp; i < n; i += kRescoreWarps) {
+        if (st.score[off + i] < floor_q) {
+            if (lane == 0) st.score[off + i] = -std::numeric_limits<float>::infinity();
+            continue;
+        }
         const float* __restrict__ d = df + (size_t)st.id[off + i] * dim;
         float acc = 0.f;
         if ((dim & 3) == 0) {
@@ -408,21 +416,9 @@ size_t fz_dense_topk_workspace_bytes(int n_queries, int k, int cap) {
     return cand_state_bytes<float>(n_queries, cap);
 }
 
-int fz_dense_topk(const void* q_bf16, const void* d_bf16, const float* q_f32, const float* d_f32, int n_queries,
-                  int64_t n_docs, int dim, int k, float margin, int64_t doc_base, int cap, int growth,
-                  float* out_scores, int32_t* out_ids, int32_t* out_status, void* ws, size_t ws_bytes,
-                  fz_stream_t stream_) {
-    cudaStream_t stream = (cudaStream_t)stream_;
-    FZ_REQUIRE(q_bf16 && d_bf16 && out_scores && out_ids && out_status, "null pointer");
-    FZ_REQUIRE((q_f32 == nullptr) == (d_f32 == nullptr), "q_f32 and d_f32 must both be given (exact) or both NULL (bf16)");
-    FZ_REQUIRE(dim >= 64 && dim % 64 == 0, "dim=%d must be a positive multiple of 64 (pad with zeros)", dim);
-    FZ_REQUIRE(n_docs >= 1 && n_docs < (1ll << 31), "n_docs out of range");
-    FZ_REQUIRE(k >= 1 && cap >= 2 * k && cap <= 8192, "need 1 <= k, 2k <= cap <= 8192 (k=%d cap=%d)", k, cap);
-    FZ_REQUIRE(growth >= 1 && growth <= 64, "growth=%d out of range", growth);
-    FZ_REQUIRE(margin >= 0.f, "margin must be >= 0");
-    FZ_REQUIRE(ws && ws_bytes >= cand_state_bytes<float>(n_queries, cap), "workspace too small");
-    if (n_queries == 0) return FZ_OK;
-
+static int dense_filter_phase(const void* q_bf16, const void* d_bf16, bool exact, int n_queries, int64_t n_docs, int dim,
+                              int k, float margin, int64_t doc_base, int cap, int growth, float* out_scores,
+                              int32_t* out_ids, int32_t* out_status, void* ws, cudaStream_t stream) {
     CUtensorMap tmap_q, tmap_d;
     int rc = make_bf16_tile_map(&tmap_q, q_bf16, (uint64_t)n_queries, (uint64_t)dim, kBM);
     if (rc) return rc;
@@ -433,7 +429,6 @@ int fz_dense_topk(const void* q_bf16, const void* d_bf16, const float* q_f32, co
         FZ_CUDA(cudaFuncSetAttribute(dense_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
         attr = true;
     }
-
     GemmArgs G;
     memset(&G, 0, sizeof(G));
     G.n_queries = n_queries;
@@ -443,8 +438,6 @@ int fz_dense_topk(const void* q_bf16, const void* d_bf16, const float* q_f32, co
     G.stats = (unsigned long long*)g_debug_stats;
     rc = cand_init<float>(G.st, n_queries, stream);
     if (rc) return rc;
-
-    const bool exact = d_f32 != nullptr;
     long long lo = 0, hi = n_docs < cap ? n_docs : cap;
     while (true) {
         G.r_lo = lo;
@@ -466,16 +459,77 @@ int fz_dense_topk(const void* q_bf16, const void* d_bf16, const float* q_f32, co
         hi = growth >= 2 ? hi * growth : hi + (cap - k);
         if (hi > n_docs) hi = n_docs;
     }
-    if (exact) {
-        {
-            ProfScope prof("dense_rescore_f32", stream);
-            rescore_kernel<<<n_queries, kRescoreWarps * 32, (size_t)dim * sizeof(float), stream>>>(q_f32, d_f32, dim, G.st);
-        }
-        FZ_LAUNCH_CHECK();
-        rc = cand_select<float>(G.st, n_queries, k, 0.f, true, doc_base, out_scores, out_ids, nullptr, stream);
-        if (rc) return rc;
-    }
     return FZ_OK;
+}
+
+static int dense_finish_phase(const float* q_f32, const float* d_f32, const float* tau_floor, int n_queries, int dim, int k,
+                              int64_t doc_base, int cap, float* out_scores, int32_t* out_ids, int32_t* out_status, void* ws,
+                              cudaStream_t stream) {
+    CandState<float> st = cand_state_carve<float>(ws, n_queries, cap, out_status);
+    {
+        ProfScope prof("dense_rescore_f32", stream);
+        rescore_kernel<<<n_queries, kRescoreWarps * 32, (size_t)dim * sizeof(float), stream>>>(q_f32, d_f32, dim, st, tau_floor);
+    }
+    FZ_LAUNCH_CHECK();
+    return cand_select<float>(st, n_queries, k, 0.f, true, doc_base, out_scores, out_ids, nullptr, stream);
+}
+
+static int dense_check(const void* q_bf16, const void* d_bf16, const float* q_f32, const float* d_f32, int n_queries,
+                       int64_t n_docs, int dim, int k, float margin, int cap, int growth, const float* out_scores,
+                       const int32_t* out_ids, const int32_t* out_status, const void* ws, size_t ws_bytes) {
+    FZ_REQUIRE(q_bf16 && d_bf16 && out_scores && out_ids && out_status, "null pointer");
+    FZ_REQUIRE((q_f32 == nullptr) == (d_f32 == nullptr), "q_f32 and d_f32 must both be given (exact) or both NULL (bf16)");
+    FZ_REQUIRE(dim >= 64 && dim % 64 == 0, "dim=%d must be a positive multiple of 64 (pad with zeros)", dim);
+    FZ_REQUIRE(n_docs >= 1 && n_docs < (1ll << 31), "n_docs out of range");
+    FZ_REQUIRE(k >= 1 && cap >= 2 * k && cap <= 8192, "need 1 <= k, 2k <= cap <= 8192 (k=%d cap=%d)", k, cap);
+    FZ_REQUIRE(growth >= 1 && growth <= 64, "growth=%d out of range", growth);
+    FZ_REQUIRE(margin >= 0.f, "margin must be >= 0");
+    FZ_REQUIRE(ws && ws_bytes >= cand_state_bytes<float>(n_queries, cap), "workspace too small");
+    return FZ_OK;
+}
+
+int fz_dense_topk(const void* q_bf16, const void* d_bf16, const float* q_f32, const float* d_f32, int n_queries,
+                  int64_t n_docs, int dim, int k, float margin, int64_t doc_base, int cap, int growth,
+                  float* out_scores, int32_t* out_ids, int32_t* out_status, void* ws, size_t ws_bytes,
+                  fz_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc = dense_check(q_bf16, d_bf16, q_f32, d_f32, n_queries, n_docs, dim, k, margin, cap, growth, out_scores, out_ids,
+                         out_status, ws, ws_bytes);
+    if (rc) return rc;
+    if (n_queries == 0) return FZ_OK;
+    const bool exact = d_f32 != nullptr;
+    rc = dense_filter_phase(q_bf16, d_bf16, exact, n_queries, n_docs, dim, k, margin, doc_base, cap, growth, out_scores,
+                            out_ids, out_status, ws, stream);
+    if (rc || !exact) return rc;
+    return dense_finish_phase(q_f32, d_f32, nullptr, n_queries, dim, k, doc_base, cap, out_scores, out_ids, out_status, ws, stream);
+}
+
+int fz_dense_topk_filter(const void* q_bf16, const void* d_bf16, int n_queries, int64_t n_docs, int dim, int k, float margin,
+                         int64_t doc_base, int cap, int growth, float* out_tau, int32_t* out_status, void* ws,
+                         size_t ws_bytes, fz_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    FZ_REQUIRE(out_tau, "null pointer");
+    int rc = dense_check(q_bf16, d_bf16, nullptr, nullptr, n_queries, n_docs, dim, k, margin, cap, growth, out_tau,
+                         out_status, out_status, ws, ws_bytes);
+    if (rc) return rc;
+    if (n_queries == 0) return FZ_OK;
+    rc = dense_filter_phase(q_bf16, d_bf16, true, n_queries, n_docs, dim, k, margin, doc_base, cap, growth, nullptr, nullptr,
+                            out_status, ws, stream);
+    if (rc) return rc;
+    const CandState<float> st = cand_state_carve<float>(ws, n_queries, cap, out_status);
+    FZ_CUDA(cudaMemcpyAsync(out_tau, st.tau, sizeof(float) * (size_t)n_queries, cudaMemcpyDeviceToDevice, stream));
+    return FZ_OK;
+}
+
+int fz_dense_topk_finish(const float* q_f32, const float* d_f32, const float* tau_floor, int n_queries, int dim, int k,
+                         int64_t doc_base, int cap, float* out_scores, int32_t* out_ids, int32_t* out_status, void* ws,
+                         size_t ws_bytes, fz_stream_t stream_) {
+    FZ_REQUIRE(q_f32 && d_f32 && out_scores && out_ids && out_status, "null pointer");
+    FZ_REQUIRE(k >= 1 && cap >= 2 * k && cap <= 8192 && dim >= 1, "bad sizes");
+    FZ_REQUIRE(ws && ws_bytes >= cand_state_bytes<float>(n_queries, cap), "workspace too small");
+    if (n_queries == 0) return FZ_OK;
+    return dense_finish_phase(q_f32, d_f32, tau_floor, n_queries, dim, k, doc_base, cap, out_scores, out_ids, out_status, ws,
+                              (cudaStream_t)stream_);
 }
 
 int fz_dense_scores_f32(const float* q_f32, const float* d_f32, int n_queries, int64_t n_docs, int dim,

@@ -379,11 +379,13 @@ def normalize_rows(x: torch.Tensor, normalize: bool = True, want_f32: bool = Tru
 
 
 def dense_topk(q_bf16, d_bf16, q_f32, d_f32, k: int, margin: float = 0.0, doc_base: int = 0,
-               cap: int = DEFAULT_CAP, growth: int = DEFAULT_GROWTH):
+               cap: int = DEFAULT_CAP, growth: int = DEFAULT_GROWTH, tau_reduce=None):
     """Exhaustive inner-product top-k (tcgen05 GEMM with the threshold filter in its epilogue).
 
     q_bf16 [Q, d], d_bf16 [N, d] are the tensor-core operands; with q_f32 / d_f32 the survivors within ``margin`` of
-    the running k-th bf16 score are rescored in fp32 (exact mode).  -> (scores f32 [Q,k], ids int32 [Q,k])."""
+    the running k-th bf16 score are rescored in fp32 (exact mode).  -> (scores f32 [Q,k], ids int32 [Q,k]).
+    ``tau_reduce`` (corpus-sharded exact mode): a callable that maximises the per-query thresholds [Q] over the shards
+    (one all-reduce); candidates below the best shard's threshold are then not rescored."""
     lib = _lib.load()
     q_bf16 = _req(q_bf16, torch.bfloat16, "q_bf16")
     d_bf16 = _req(d_bf16, torch.bfloat16, "d_bf16")
@@ -399,12 +401,19 @@ def dense_topk(q_bf16, d_bf16, q_f32, d_f32, k: int, margin: float = 0.0, doc_ba
     out_i = torch.empty((nq, k_eff), dtype=torch.int32, device=q_bf16.device)
     status = torch.empty((nq,), dtype=torch.int32, device=q_bf16.device)
     ws = _ws(lib.fz_dense_topk_workspace_bytes(nq, k_eff, cap), q_bf16.device)
+    staged = exact and tau_reduce is not None
+    tau = torch.empty((nq,), dtype=torch.float32, device=q_bf16.device) if staged else None
 
     def run(g):
-        check(lib.fz_dense_topk(_ptr(q_bf16), _ptr(d_bf16), _ptr(q_f32 if exact else None),
-                                _ptr(d_f32 if exact else None), nq, n, dim, k_eff, float(margin), doc_base, cap, g,
-                                _ptr(out_s), _ptr(out_i), _ptr(status), _ptr(ws), ws.numel(), _stream(out_s)),
-              "fz_dense_topk")
+        if staged:
+            check(lib.fz_dense_topk_filter(_ptr(q_bf16), _ptr(d_bf16), nq, n, dim, k_eff, float(margin), doc_base, cap, g,
+                                           _ptr(tau), _ptr(status), _ptr(ws), ws.numel(), _stream(out_s)),
+                  "fz_dense_topk_filter")
+        else:
+            check(lib.fz_dense_topk(_ptr(q_bf16), _ptr(d_bf16), _ptr(q_f32 if exact else None),
+                                    _ptr(d_f32 if exact else None), nq, n, dim, k_eff, float(margin), doc_base, cap, g,
+                                    _ptr(out_s), _ptr(out_i), _ptr(status), _ptr(ws), ws.numel(), _stream(out_s)),
+                  "fz_dense_topk")
 
     # With a margin every round emits everything within `margin` of the running k-th score, about twice the k
     # survivors of the plain filter, so the doc ranges may only grow 3x per round instead of 4x.
@@ -418,6 +427,11 @@ def dense_topk(q_bf16, d_bf16, q_f32, d_f32, k: int, margin: float = 0.0, doc_ba
                 raise FusionB200Error("dense top-k candidate buffer overflowed: lower `margin` or raise `cap`")
         else:
             run(1)      # conservative rounds never overflow when margin == 0
+    if staged:
+        floor = tau_reduce(tau)
+        check(lib.fz_dense_topk_finish(_ptr(q_f32), _ptr(d_f32), _ptr(floor), nq, dim, k_eff, doc_base, cap, _ptr(out_s),
+                                       _ptr(out_i), _ptr(status), _ptr(ws), ws.numel(), _stream(out_s)),
+              "fz_dense_topk_finish")
     return out_s, out_i
 
 

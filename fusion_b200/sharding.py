@@ -48,6 +48,14 @@ def allreduce_lexical_stats(n_local: int, df_local: np.ndarray, sum_dl_local: in
     return int(t[0]), t[2:].numpy(), int(t[1])
 
 
+def allreduce_max(t: torch.Tensor, group=None) -> torch.Tensor:
+    """Element-wise maximum over the ranks (in place): the cross-shard threshold of the exact dense mode."""
+    world, _ = _world(group)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return t
+
+
 def gather_topk(scores: torch.Tensor, ids: torch.Tensor, group=None):
     """All-gather local top-k lists: [Q, k] -> [G, Q, k] (one collective per tensor)."""
     world, _ = _world(group)
