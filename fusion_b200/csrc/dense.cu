@@ -505,7 +505,7 @@ int fz_dense_topk(const void* q_bf16, const void* d_bf16, const float* q_f32, co
 }
 
 int fz_dense_topk_filter(const void* q_bf16, const void* d_bf16, int n_queries, int64_t n_docs, int dim, int k, float margin,
-                         int64_t doc_base, int cap, int growth, float* out_tau, int32_t* out_status, void* ws,
+                         int64_t doc_base, int cap, int growth, int floor_rank, float* out_tau, int32_t* out_status, void* ws,
                          size_t ws_bytes, fz_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     FZ_REQUIRE(out_tau, "null pointer");
@@ -516,9 +516,9 @@ int fz_dense_topk_filter(const void* q_bf16, const void* d_bf16, int n_queries, 
     rc = dense_filter_phase(q_bf16, d_bf16, true, n_queries, n_docs, dim, k, margin, doc_base, cap, growth, nullptr, nullptr,
                             out_status, ws, stream);
     if (rc) return rc;
+    FZ_REQUIRE(floor_rank >= 1 && floor_rank <= k, "floor_rank=%d must be in [1, k]", floor_rank);
     const CandState<float> st = cand_state_carve<float>(ws, n_queries, cap, out_status);
-    FZ_CUDA(cudaMemcpyAsync(out_tau, st.tau, sizeof(float) * (size_t)n_queries, cudaMemcpyDeviceToDevice, stream));
-    return FZ_OK;
+    return cand_kth_score(st, n_queries, floor_rank, margin, out_tau, stream);
 }
 
 int fz_dense_topk_finish(const float* q_f32, const float* d_f32, const float* tau_floor, int n_queries, int dim, int k,

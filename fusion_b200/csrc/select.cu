@@ -255,6 +255,42 @@ __global__ void __launch_bounds__(SelectCfg<ST>::threads, SelectCfg<ST>::blocks)
     }
 }
 
+// out[q] = (rank-th best score in query q's candidate buffer) - margin, or -inf when it holds fewer than `rank` records;
+// the buffer is left untouched (the cross-shard rescoring floor of the exact dense mode)
+__global__ void __launch_bounds__(512) cand_kth_kernel(CandState<float> st, int rank, float margin, float* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t* s_hi = reinterpret_cast<uint32_t*>(smem_raw);
+    uint32_t* s_lo = s_hi + st.cap;
+    __shared__ int s_hist[256];
+    __shared__ int s_bcast[4];
+    const int q = blockIdx.x;
+    const int n = min(st.cnt[q], st.cap);
+    if (n < rank) {
+        if (threadIdx.x == 0) out[q] = -std::numeric_limits<float>::infinity();
+        return;
+    }
+    const size_t off = (size_t)q * st.cap;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        s_hi[i] = (uint32_t)score_key(st.score[off + i]);
+        s_lo[i] = ~(uint32_t)st.id[off + i];
+    }
+    __syncthreads();
+    uint32_t kth_hi = 0, kth_lo = 0;
+    cta_radix_select_kth<uint32_t>(s_hi, s_lo, n, rank, s_hist, s_bcast, kth_hi, kth_lo);
+    if (threadIdx.x == 0) out[q] = unord32(kth_hi) - margin;
+}
+
+int cand_kth_score(const CandState<float>& st, int n_queries, int rank, float margin, float* out, cudaStream_t stream) {
+    static bool attr = false;
+    if (!attr) {
+        FZ_CUDA(cudaFuncSetAttribute(cand_kth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        attr = true;
+    }
+    cand_kth_kernel<<<n_queries, 512, (size_t)st.cap * 8, stream>>>(st, rank, margin, out);
+    FZ_LAUNCH_CHECK();
+    return FZ_OK;
+}
+
 template <typename ST>
 int cand_init(const CandState<ST>& st, int n_queries, cudaStream_t stream) {
     cand_init_kernel<ST><<<ceil_div(n_queries, 256), 256, 0, stream>>>(st, n_queries);

@@ -75,4 +75,7 @@ template <typename ST>
 int cand_select(const CandState<ST>& st, int n_queries, int k, ST margin, bool final_out, int64_t doc_base,
                 ST* out_scores, int32_t* out_ids, int32_t* out_n, cudaStream_t stream);
 
+// (rank-th best score of every query's buffer) - margin -> out [n_queries]; the buffers are not modified
+int cand_kth_score(const CandState<float>& st, int n_queries, int rank, float margin, float* out, cudaStream_t stream);
+
 }  // namespace fz

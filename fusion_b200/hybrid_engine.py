@@ -102,12 +102,12 @@ class HybridSearcher:
             def run_dense():
                 q32, q16 = self.dense.prepare_queries(q.dense)
                 exact = self.dense_exact and self.dense.d_f32 is not None
-                # sharded exact mode: the best shard's k-th score bounds the global one, so the shards agree on a floor
-                # (one all-reduce of Q floats) and rescore only what can still reach the global top-k
-                reduce = (lambda t: sharding.allreduce_max(t, self.group)) if (exact and self.world > 1) else None
+                # sharded exact mode: the shards' ceil(k/G)-th scores bound the global k-th one from below, so they agree on
+                # a floor (one all-reduce of Q floats) and rescore only what can still reach the global top-k
+                reduce = (lambda t: sharding.allreduce_min(t, self.group)) if (exact and self.world > 1) else None
                 return ops.dense_topk(q16, self.dense.d_bf16, q32 if exact else None, self.dense.d_f32 if exact else None,
                                       self.k, margin=self._dense_margin() if exact else 0.0, doc_base=self.dense.doc_base,
-                                      tau_reduce=reduce)
+                                      tau_reduce=reduce, n_shards=self.world)
             s, i = self._timed("dpr", run_dense)
             out["dpr"] = self._timed("dpr_merge", lambda: self._merge(s, i))
         if self.tokens is not None:

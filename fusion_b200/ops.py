@@ -379,13 +379,14 @@ def normalize_rows(x: torch.Tensor, normalize: bool = True, want_f32: bool = Tru
 
 
 def dense_topk(q_bf16, d_bf16, q_f32, d_f32, k: int, margin: float = 0.0, doc_base: int = 0,
-               cap: int = DEFAULT_CAP, growth: int = DEFAULT_GROWTH, tau_reduce=None):
+               cap: int = DEFAULT_CAP, growth: int = DEFAULT_GROWTH, tau_reduce=None, n_shards: int = 1):
     """Exhaustive inner-product top-k (tcgen05 GEMM with the threshold filter in its epilogue).
 
     q_bf16 [Q, d], d_bf16 [N, d] are the tensor-core operands; with q_f32 / d_f32 the survivors within ``margin`` of
     the running k-th bf16 score are rescored in fp32 (exact mode).  -> (scores f32 [Q,k], ids int32 [Q,k]).
-    ``tau_reduce`` (corpus-sharded exact mode): a callable that maximises the per-query thresholds [Q] over the shards
-    (one all-reduce); candidates below the best shard's threshold are then not rescored."""
+    ``tau_reduce`` (exact mode, corpus sharded over ``n_shards``): a callable that takes the element-wise MINIMUM of a [Q]
+    tensor over the shards (one all-reduce).  Every shard reports its ceil(k / n_shards)-th best score; the minimum
+    bounds the global k-th score from below, and candidates under it (minus the margin) are not rescored."""
     lib = _lib.load()
     q_bf16 = _req(q_bf16, torch.bfloat16, "q_bf16")
     d_bf16 = _req(d_bf16, torch.bfloat16, "d_bf16")
@@ -407,7 +408,8 @@ def dense_topk(q_bf16, d_bf16, q_f32, d_f32, k: int, margin: float = 0.0, doc_ba
     def run(g):
         if staged:
             check(lib.fz_dense_topk_filter(_ptr(q_bf16), _ptr(d_bf16), nq, n, dim, k_eff, float(margin), doc_base, cap, g,
-                                           _ptr(tau), _ptr(status), _ptr(ws), ws.numel(), _stream(out_s)),
+                                           min(k_eff, -(-k // max(1, n_shards))), _ptr(tau), _ptr(status), _ptr(ws),
+                                           ws.numel(), _stream(out_s)),
                   "fz_dense_topk_filter")
         else:
             check(lib.fz_dense_topk(_ptr(q_bf16), _ptr(d_bf16), _ptr(q_f32 if exact else None),

@@ -48,11 +48,11 @@ def allreduce_lexical_stats(n_local: int, df_local: np.ndarray, sum_dl_local: in
     return int(t[0]), t[2:].numpy(), int(t[1])
 
 
-def allreduce_max(t: torch.Tensor, group=None) -> torch.Tensor:
-    """Element-wise maximum over the ranks (in place): the cross-shard threshold of the exact dense mode."""
+def allreduce_min(t: torch.Tensor, group=None) -> torch.Tensor:
+    """Element-wise minimum over the ranks (in place): the cross-shard rescoring floor of the exact dense mode."""
     world, _ = _world(group)
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
     return t
 
 

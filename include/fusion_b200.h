@@ -222,13 +222,15 @@ int fz_dense_topk(const void* q_bf16, const void* d_bf16, const float* q_f32, co
                   int64_t n_docs, int dim, int k, float margin, int64_t doc_base, int cap, int growth,
                   float* out_scores, int32_t* out_ids, int32_t* out_status, void* ws, size_t ws_bytes,
                   fz_stream_t stream);
-/* The exact mode in two calls, for corpus-sharded runs: _filter leaves the surviving candidates in `ws` and writes every
- * query's threshold (running k-th bf16 score minus margin) to out_tau; the caller takes the maximum over the shards
- * (one all-reduce) and passes it to _finish as tau_floor: candidates below it cannot be in the global top-k and are not
- * rescored.  fz_dense_topk == _filter + _finish(tau_floor = NULL). */
+/* The exact mode in two calls, for corpus-sharded runs over G shards: _filter leaves the surviving candidates in `ws` and
+ * writes, per query, (the floor_rank-th best bf16 score of this shard) - margin to out_tau (-inf if the shard has fewer).
+ * With floor_rank = ceil(k / G) the MINIMUM of out_tau over the shards (one all-reduce) is a lower bound of
+ * (global k-th bf16 score) - margin: the G shards' best ceil(k / G) are >= k documents.  Passed to _finish as tau_floor,
+ * it spares the fp32 rescoring (a 3 KB row each) of every candidate that cannot reach the global top-k.
+ * fz_dense_topk == _filter + _finish(tau_floor = NULL). */
 int fz_dense_topk_filter(const void* q_bf16, const void* d_bf16, int n_queries, int64_t n_docs, int dim, int k, float margin,
-                         int64_t doc_base, int cap, int growth, float* out_tau, int32_t* out_status, void* ws,
-                         size_t ws_bytes, fz_stream_t stream);
+                         int64_t doc_base, int cap, int growth, int floor_rank, float* out_tau, int32_t* out_status,
+                         void* ws, size_t ws_bytes, fz_stream_t stream);
 int fz_dense_topk_finish(const float* q_f32, const float* d_f32, const float* tau_floor, int n_queries, int dim, int k,
                          int64_t doc_base, int cap, float* out_scores, int32_t* out_ids, int32_t* out_status, void* ws,
                          size_t ws_bytes, fz_stream_t stream);
