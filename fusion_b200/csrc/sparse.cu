@@ -88,9 +88,8 @@ struct TermStatic {
 // The terms with at least one posting in the current tile, dense ones first for fp32 (query order for fp64).
 struct TermList {
     long long lo[kMaxTerms];
-    int len[kMaxTerms];
-    int kind[kMaxTerms];
-    float w[kMaxTerms];
+    int lenkind[kMaxTerms];                  // postings in the tile | storage form << 24
+    float w[kMaxTerms];                      // fp32 only
     unsigned ballot[kMaxTerms / 32][2];      // [warp][0 = active dense, 1 = active scatter]
     int n;
 };
@@ -152,9 +151,12 @@ __device__ __forceinline__ void resolve_terms(const SparseArgs<AccT>& A, int q, 
 // takes all dense terms first.  Terms with no posting in the tile are dropped when the tile's term list is built.
 // (o0, o1) are this thread's term's segment bounds in the tile (tiled terms), loaded one tile ahead by the caller.
 // acc needs kVec * kChunks * blockDim + 4 slots; slot tile_docs is the dump slot of the padding postings.
-template <typename AccT>
+// The final sums of this thread's docs are returned in racc (kToSmem = false: the caller scans them in registers, so a
+// tile that ends on a dense term never goes through shared memory) or left in acc behind a barrier (kToSmem = true).
+template <typename AccT, bool kToSmem>
 __device__ __forceinline__ void accumulate_tile(const SparseArgs<AccT>& A, int tile, long long d_lo, AccT* acc,
-                                                const TermStatic& S, TermList& L, uint32_t o0, uint32_t o1) {
+                                                const TermStatic& S, TermList& L, uint32_t o0, uint32_t o1,
+                                                typename std::conditional<std::is_same<AccT, double>::value, double2, float4>::type (&racc)[kChunks]) {
     constexpr int kVec = AccTraits<AccT>::kVec;
     constexpr bool kF64 = std::is_same<AccT, double>::value;
     using Vec = typename std::conditional<kF64, double2, float4>::type;
@@ -166,11 +168,13 @@ __device__ __forceinline__ void accumulate_tile(const SparseArgs<AccT>& A, int t
     const int tile_docs = A.ix.tile_docs;
     const int dl = (int)d_lo;
 
-    // ---- the tile's term list (threads 0 .. kMaxTerms-1 hold one term each; every CTA has at least that many)
+    // ---- the tile's term list: thread i < n_terms holds term i; only the warps that hold terms take part, and a query
+    // of <= 32 terms (every lexical query) needs no exchange between warps, so its list costs one barrier per tile
+    const int n_tw = S.n <= 32 ? 1 : (S.n + 31) >> 5;
     long long lo = 0;
     int len = 0, kind = kKindNone;
     unsigned bd = 0, bs = 0;
-    if (t < kMaxTerms) {
+    if (t < 32 * n_tw) {
         kind = S.kind[t];
         if (kind == kKindTiled) {
             lo = S.base[t] + o0;
@@ -184,34 +188,35 @@ __device__ __forceinline__ void accumulate_tile(const SparseArgs<AccT>& A, int t
         }
         bd = __ballot_sync(0xffffffffu, len > 0 && kind == kKindDense);
         bs = __ballot_sync(0xffffffffu, len > 0 && kind != kKindDense);
-        if ((t & 31) == 0) { L.ballot[t >> 5][0] = bd; L.ballot[t >> 5][1] = bs; }
+        if (n_tw > 1 && (t & 31) == 0) { L.ballot[t >> 5][0] = bd; L.ballot[t >> 5][1] = bs; }
     }
-    __syncthreads();
-    if (t < kMaxTerms) {
+    if (n_tw > 1) __syncthreads();
+    if (t < 32 * n_tw) {
         const int wi = t >> 5;
         const unsigned below = (1u << (t & 31)) - 1;
-        int dense_before = __popc(bd & below), scat_before = __popc(bs & below), n_dense = 0, n_scat = 0;
-#pragma unroll
-        for (int w2 = 0; w2 < kMaxTerms / 32; ++w2) {
-            const int nd = __popc(L.ballot[w2][0]), ns = __popc(L.ballot[w2][1]);
-            if (w2 < wi) { dense_before += nd; scat_before += ns; }
-            n_dense += nd;
-            n_scat += ns;
+        int dense_before = __popc(bd & below), scat_before = __popc(bs & below), n_dense = __popc(bd), n_scat = __popc(bs);
+        if (n_tw > 1) {
+            n_dense = 0;
+            n_scat = 0;
+            for (int w2 = 0; w2 < n_tw; ++w2) {
+                const int nd = __popc(L.ballot[w2][0]), ns = __popc(L.ballot[w2][1]);
+                if (w2 < wi) { dense_before += nd; scat_before += ns; }
+                n_dense += nd;
+                n_scat += ns;
+            }
         }
         if (len > 0) {
             int pos;
             if (kF64) pos = dense_before + scat_before;                       // query order
             else pos = kind == kKindDense ? dense_before : n_dense + scat_before;
             L.lo[pos] = lo;
-            L.len[pos] = len;
-            L.kind[pos] = kind;
-            L.w[pos] = S.w[t];
+            L.lenkind[pos] = len | (kind << 24);
+            if (!kF64) L.w[pos] = S.w[t];
         }
         if (t == 0) L.n = n_dense + n_scat;
     }
     __syncthreads();
 
-    Vec racc[kChunks];
 #pragma unroll
     for (int c = 0; c < kChunks; ++c) {
         if constexpr (kF64) racc[c] = make_double2(0.0, 0.0); else racc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -222,9 +227,10 @@ __device__ __forceinline__ void accumulate_tile(const SparseArgs<AccT>& A, int t
     // were both measured slower: the extra registers cost more occupancy than the shorter dependency chain wins.)
     const int n_active = L.n;
     for (int j = 0; j < n_active; ++j) {
-        const int jlen = L.len[j];
-        const int jkind = L.kind[j];
-        const float jw = L.w[j];
+        const int jlk = L.lenkind[j];
+        const int jlen = jlk & 0xffffff;
+        const int jkind = jlk >> 24;
+        const float jw = kF64 ? 1.0f : L.w[j];
         const long long jlo = L.lo[j];
         if (jkind == kKindDense) {
             if (!in_reg) {      // the last scatter ended with a barrier
@@ -283,11 +289,20 @@ __device__ __forceinline__ void accumulate_tile(const SparseArgs<AccT>& A, int t
         }
         __syncthreads();   // the next term may hit the same docs
     }
-    if (in_reg) {
+    if constexpr (kToSmem) {
+        if (in_reg) {
 #pragma unroll
-        for (int c = 0; c < kChunks; ++c) *reinterpret_cast<Vec*>(acc + (size_t)(c * T + t) * kVec) = racc[c];
+            for (int c = 0; c < kChunks; ++c) *reinterpret_cast<Vec*>(acc + (size_t)(c * T + t) * kVec) = racc[c];
+        }
+        __syncthreads();
+    } else {
+        // the caller scans this thread's docs in registers: a tile that ends on a dense term (or holds only dense
+        // terms) never touches shared memory again
+        if (!in_reg) {
+#pragma unroll
+            for (int c = 0; c < kChunks; ++c) racc[c] = *reinterpret_cast<const Vec*>(acc + (size_t)(c * T + t) * kVec);
+        }
     }
-    __syncthreads();
 }
 
 // segment bounds of this thread's term in `tile` (tiled terms only)
@@ -303,47 +318,50 @@ __device__ __forceinline__ uint32_t tile_offset(const SparseArgs<AccT>& A, const
 // stream the same slice of the posting lists at the same time and the slice is served from L2 / L1).
 template <typename AccT, int MODE>   // MODE 0: threshold emit, 1: store every score
 __global__ void __launch_bounds__(kMaxSparseThreads) sparse_tile_kernel(const SparseArgs<AccT> A) {
+    constexpr int kVec = AccTraits<AccT>::kVec;
+    using Vec = typename std::conditional<std::is_same<AccT, double>::value, double2, float4>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     AccT* acc = reinterpret_cast<AccT*>(smem_raw);
     __shared__ TermStatic S;
-    __shared__ TermList L;
+    __shared__ TermList L[2];     // double-buffered: a warp may build the next tile's list while others still read this one
 
     const int group = A.group_lo + blockIdx.x / A.n_queries;
     const int q = blockIdx.x % A.n_queries;
     const int t_begin = max(group * kGroupTiles, A.tile_lo), t_end = min((group + 1) * kGroupTiles, A.tile_hi);
     resolve_terms<AccT>(A, q, group, S);
     const AccT tau = MODE == 0 ? A.st.tau[q] : (AccT)0;
+    const AccT lim = A.sign_mode > 0 ? (tau > (AccT)0 ? tau : (AccT)0) : tau;
     __syncthreads();
     uint32_t o0 = tile_offset<AccT>(A, S, t_begin), o1 = tile_offset<AccT>(A, S, t_begin + 1);
     for (int tile = t_begin; tile < t_end; ++tile) {
         const uint32_t o2 = tile + 1 < t_end ? tile_offset<AccT>(A, S, tile + 2) : 0;      // next tile's bound, in flight
         const long long d_lo = (long long)tile * A.ix.tile_docs;
         const long long d_hi = min(d_lo + A.ix.tile_docs, (long long)A.ix.n_docs);
-        accumulate_tile<AccT>(A, tile, d_lo, acc, S, L, o0, o1);
+        Vec racc[kChunks];
+        accumulate_tile<AccT, false>(A, tile, d_lo, acc, S, L[tile & 1], o0, o1, racc);
         o0 = o1;
         o1 = o2;
-        if (MODE == 1) {
-            const int n = (int)(d_hi - d_lo);
-            AccT* out = A.out_full + (size_t)q * A.ix.n_docs + d_lo;
-            for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = acc[i];
-        } else {
-            // emit only the docs of this round; a tile that straddles a round boundary is accumulated by both rounds
-            const int e_lo = (int)(max(d_lo, A.r_lo) - d_lo), e_hi = (int)(min(d_hi, A.r_hi) - d_lo);
-            // scan the tile 16 bytes at a time; survivors are rare once tau has risen: the common case is one compare
-            constexpr int V = 16 / (int)sizeof(AccT);
-            const AccT lim = A.sign_mode > 0 ? (tau > (AccT)0 ? tau : (AccT)0) : tau;
-            for (int i0 = (e_lo / V) * V + threadIdx.x * V; i0 < e_hi; i0 += blockDim.x * V) {
-                AccT v[V];
-                *reinterpret_cast<int4*>(v) = *reinterpret_cast<const int4*>(acc + i0);
+        // every thread scans its own docs in registers; survivors are rare once tau has risen
+        // (a tile that straddles a round boundary is accumulated by both rounds and emitted once: [e_lo, e_hi))
+        const int e_lo = MODE == 1 ? 0 : (int)(max(d_lo, A.r_lo) - d_lo);
+        const int e_hi = MODE == 1 ? (int)(d_hi - d_lo) : (int)(min(d_hi, A.r_hi) - d_lo);
 #pragma unroll
-                for (int u = 0; u < V; ++u) {
-                    const AccT sc = v[u];
+        for (int c = 0; c < kChunks; ++c) {
+            const int i0 = (c * (int)blockDim.x + (int)threadIdx.x) * kVec;
+            AccT v[kVec];
+            *reinterpret_cast<Vec*>(v) = racc[c];
+#pragma unroll
+            for (int u = 0; u < kVec; ++u) {
+                const AccT sc = v[u];
+                const bool inside = i0 + u >= e_lo && i0 + u < e_hi;
+                if (MODE == 1) {
+                    if (inside) A.out_full[(size_t)q * A.ix.n_docs + d_lo + i0 + u] = sc;
+                } else {
                     const bool want = A.sign_mode > 0 ? (sc > lim) : (sc < (AccT)0 && sc > lim);
-                    if (want && i0 + u >= e_lo && i0 + u < e_hi) cand_append<AccT>(A.st, q, sc, (int32_t)(d_lo + i0 + u));
+                    if (want && inside) cand_append<AccT>(A.st, q, sc, (int32_t)(d_lo + i0 + u));
                 }
             }
         }
-        // the next tile's term list is written only after its first barrier, which every thread reaches after this scan
     }
 }
 
@@ -351,6 +369,7 @@ __global__ void __launch_bounds__(kMaxSparseThreads) sparse_tile_kernel(const Sp
 // (the reference ranks every document; unmatched ones score exactly 0.0 and tie by index, bm25.py:103-105).
 template <typename AccT>
 __global__ void __launch_bounds__(kMaxSparseThreads) sparse_zero_fill_kernel(const SparseArgs<AccT> A) {
+    using Vec = typename std::conditional<std::is_same<AccT, double>::value, double2, float4>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     AccT* acc = reinterpret_cast<AccT*>(smem_raw);
     __shared__ TermStatic S;
@@ -377,7 +396,8 @@ __global__ void __launch_bounds__(kMaxSparseThreads) sparse_zero_fill_kernel(con
         }
         const long long d_lo = (long long)tile * A.ix.tile_docs;
         const long long d_hi = min(d_lo + A.ix.tile_docs, (long long)A.ix.n_docs);
-        accumulate_tile<AccT>(A, tile, d_lo, acc, S, L, tile_offset<AccT>(A, S, tile), tile_offset<AccT>(A, S, tile + 1));
+        Vec racc[kChunks];
+        accumulate_tile<AccT, true>(A, tile, d_lo, acc, S, L, tile_offset<AccT>(A, S, tile), tile_offset<AccT>(A, S, tile + 1), racc);
         const int n = (int)(d_hi - d_lo);
         for (int c0 = 0; c0 < n; c0 += blockDim.x) {
             const int i = c0 + threadIdx.x;
