@@ -52,6 +52,10 @@ SIGNATURES = {
     "fz_token_starts": (_i, [_p, _i64, _p, _p]),
     "fz_hash_tokens": (_i, [_p, _i64, _p, _i64, _p, _p, _p, _p]),
     "fz_quantiles_f64": (_i, [_p, _i64, _i, _p, _p]),
+    "fz_splade_pool": (_i, [_p, _i, _p, _i, _i, _i, _i, _p, _p]),
+    "fz_prune_topk": (_i, [_p, _i, _i, _i, _p, _p]),
+    "fz_csr_count": (_i, [_p, _i, _i, _p, _p]),
+    "fz_csr_fill": (_i, [_p, _i, _i, _p, _p, _p, _p]),
     "fz_lexical_impacts": (_i, [_p, _p, _p, _p, _p, C.c_int32, _i64, _d, _d, _d, _i, _p, _p]),
     "fz_sparse_topk_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "fz_sparse_topk_f64": (_i, [_p, _p, _p, _i, _i, _i64, _i, _i, _i, _p, _p, _p, _p, _sz, _p]),

@@ -309,7 +309,7 @@ __device__ __forceinline__ void accumulate_tile(const SparseArgs<AccT>& A, int t
 template <typename AccT>
 __device__ __forceinline__ uint32_t tile_offset(const SparseArgs<AccT>& A, const TermStatic& S, int tile) {
     const int t = threadIdx.x;
-    if (t < kMaxTerms && S.kind[t] == kKindTiled)
+    if (t < max(S.n, 1) && S.kind[t] == kKindTiled)
         return __ldg(A.ix.tiled_tile_off + (size_t)S.aux[t] * (A.ix.n_tiles + 1) + tile);
     return 0;
 }

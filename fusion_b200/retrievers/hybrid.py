@@ -134,14 +134,10 @@ class Ranker:
     @staticmethod
     def sparse_vector_search_tensors(q_acts: torch.Tensor, d_acts: torch.Tensor, top_k: int, similarity: str = "cos_sim"):
         """SPLADE activations [*, V] (mostly zeros, splade.py:88-99) -> CSR -> inverted-index scoring."""
-        def to_csr(x):
-            nz = torch.nonzero(x)
-            ptr = torch.zeros(x.shape[0] + 1, dtype=torch.int64, device=x.device)
-            ptr[1:] = torch.cumsum(torch.bincount(nz[:, 0], minlength=x.shape[0]), 0)
-            return ptr, nz[:, 1], x[nz[:, 0], nz[:, 1]].float()
-        dp, dt, dw = to_csr(d_acts)
-        index = SparseIndex(dp, dt, dw, d_acts.shape[1], similarity, device=d_acts.device)
-        qp, qt, qw = sparse_queries(*to_csr(q_acts), similarity, d_acts.device)
+        from ..activations import activations_to_csr as to_csr         # csrc/activations.cu: ordered compaction per row
+        dp, dt, dw = to_csr(d_acts.float().cuda())
+        index = SparseIndex(dp, dt, dw, d_acts.shape[1], similarity, device=dp.device)
+        qp, qt, qw = sparse_queries(*to_csr(q_acts.float().cuda()), similarity, dp.device)
         k = min(top_k, index.n_docs)
         if k >= FULL_RANKING_MIN_K or 2 * k > ops.DEFAULT_CAP:
             return ops.rank_rows(ops.sparse_scores(index.view(), qp, qt, qw), k, 0)

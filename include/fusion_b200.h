@@ -141,6 +141,25 @@ int fz_hash_tokens(const void* utf8, int64_t n_bytes, const int64_t* starts, int
 int fz_quantiles_f64(const double* sorted, int64_t n, int n_quantiles, double* out, fz_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * SPLADE activation head: between the encoder's MLM logits and the CSR vectors K2 consumes.
+ * fz_splade_pool: activations[b, v] = sum_l or amax_l log1p(relu(logits[b, l, v] * mask[b, l]))
+ *   (SPLADE.forward, src/retrievers/splade/splade.py:88-94).  logits [n_rows, seq_len, vocab] fp32 or bf16, row-major;
+ *   mask [n_rows, seq_len] int32 (0 = padding: never loaded); out_act [n_rows, vocab] fp32.
+ * fz_prune_topk: keep the keep_topk largest activations of every row and zero the rest (SPLADE._prune_activations,
+ *   splade.py:295-306); ties at the cutoff keep the lower term id; out_act may alias act.
+ * fz_csr_count / fz_csr_fill: dense [n_rows, vocab] -> CSR with zeros dropped and term ids ascending.  The caller
+ *   turns out_nnz into row_ptr (exclusive prefix sum, int64 [n_rows + 1]) between the two calls.
+ * ---------------------------------------------------------------------------------------------------------- */
+#define FZ_POOL_MAX 0
+#define FZ_POOL_SUM 1
+int fz_splade_pool(const void* logits, int logits_are_bf16, const int32_t* mask, int n_rows, int seq_len, int vocab,
+                   int pooling, float* out_act, fz_stream_t stream);
+int fz_prune_topk(const float* act, int n_rows, int vocab, int keep_topk, float* out_act, fz_stream_t stream);
+int fz_csr_count(const float* act, int n_rows, int vocab, int32_t* out_nnz, fz_stream_t stream);
+int fz_csr_fill(const float* act, int n_rows, int vocab, const int64_t* row_ptr, int32_t* out_term, float* out_weight,
+                fz_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * K2  sparse scoring over a term-major CSR inverted index, document range tiled for shared-memory accumulators.
  * Replaces TFIDF/BM25/AtireBM25.score + .search (src/retrievers/bm25.py:100-115,149-156) and, for SPLADE,
  * the dense [Q,V]x[V,N] cosine of src/retrievers/hybrid.py:101-103 / splade/base.py:186-197.
@@ -175,7 +194,9 @@ typedef struct fz_postings {
     int32_t n_coarse;               /* ceil(n_tiles / FZ_COARSE_TILES) */
     int64_t n_docs;
 } fz_postings_t;
+#ifndef FZ_COARSE_TILES
 #define FZ_COARSE_TILES 16 /* also the number of consecutive tiles one CTA walks */
+#endif
 
 #define FZ_MAX_QUERY_TERMS 128
 #define FZ_LEX_TFIDF 0

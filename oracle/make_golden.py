@@ -198,8 +198,39 @@ def golden_dense():
     np.savez_compressed(os.path.join(OUT, "dense_small.npz"), **out)
 
 
+def splade_head_inputs():
+    """Seeded logits [6, 9, 517] with the cases the head must get right: padded tails, a fully padded row, one
+    unmasked position, all-negative logits, exact duplicates across the pruning cutoff."""
+    g = torch.Generator().manual_seed(77)
+    logits = torch.randn((6, 9, 517), generator=g) * 2.0
+    mask = torch.ones((6, 9), dtype=torch.int64)
+    mask[0, 5:] = 0
+    mask[1, :] = 0
+    mask[2, 1:] = 0
+    logits[3] = -logits[3].abs()
+    logits[4, :, 100:140] = logits[4, :, 60:100]          # duplicated columns: equal activations
+    return logits, mask
+
+
+def golden_splade_head():
+    logits, mask = splade_head_inputs()
+    out = {"logits": logits.numpy(), "mask": mask.numpy()}
+    for pooling in ("max", "sum"):
+        m = ref_loader.make_splade_head(logits, pooling, None)
+        act = m.forward(None, mask)
+        out[f"act_{pooling}"] = act.numpy()
+        for k in (1, 32, 517):
+            pruned, idx = m._prune_activations(act, keep_topk=k)
+            out[f"pruned_{pooling}_{k}"] = pruned.numpy()
+            out[f"topk_{pooling}_{k}"] = idx.numpy()
+        m2 = ref_loader.make_splade_head(logits, pooling, 32)
+        assert torch.equal(m2.forward(None, mask), torch.from_numpy(out[f"pruned_{pooling}_32"]))
+    np.savez_compressed(os.path.join(OUT, "splade_head_small.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    golden_splade_head()
     golden_lexical()
     golden_fusion()
     golden_sweep()

@@ -73,6 +73,42 @@ def load_splade_base():
     return importlib.import_module("src.retrievers.splade.base")
 
 
+def load_splade():
+    """-> module ``src.retrievers.splade.splade`` (class SPLADE), verbatim.  Two names the module imports no longer
+    exist where it looks for them: ``transformers.optimization.AdamW`` (removed in transformers 5; only used by
+    ``fit``) and ``BaseModel`` / ``MmarcoReader`` on the ``splade`` package (its ``__init__`` exports nothing); both
+    are set on the imported modules, the reference sources stay untouched."""
+    base = load_splade_base()
+    import importlib
+    import torch
+    import transformers.optimization as opt
+    if not hasattr(opt, "AdamW"):
+        opt.AdamW = torch.optim.AdamW
+    pkg = importlib.import_module("src.retrievers.splade")
+    if not hasattr(pkg, "BaseModel"):
+        pkg.BaseModel = base.BaseModel
+    if not hasattr(pkg, "MmarcoReader"):
+        pkg.MmarcoReader = type("MmarcoReader", (), {})
+    return importlib.import_module("src.retrievers.splade.splade")
+
+
+def make_splade_head(logits, pooling: str, pruning_topk):
+    """A verbatim ``SPLADE`` whose encoder is a stub returning ``logits``: ``forward`` (splade.py:80-99) and
+    ``_prune_activations`` (:295-306) then run unmodified."""
+    import types
+    import torch
+    mod = load_splade()
+
+    class _Encoder(torch.nn.Module):
+        def forward(self, input_ids=None, attention_mask=None):
+            return types.SimpleNamespace(logits=logits)
+
+    m = object.__new__(mod.SPLADE)
+    torch.nn.Module.__init__(m)
+    m.model, m.pooling, m.pruning_topk, m.relu, m.device = _Encoder(), pooling, pruning_topk, torch.nn.ReLU(), "cpu"
+    return m
+
+
 def make_injected_searcher(similarity: str, q_embs, d_embs):
     """A verbatim ``BaseModel`` whose ``encode`` returns injected tensors, so that
     ``BaseModel.search`` (splade/base.py:199-251) runs unmodified on synthetic embeddings."""

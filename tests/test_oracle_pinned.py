@@ -111,3 +111,22 @@ def test_distribution_oracle_matches_pandas_golden(golden_dir):
     for s in ("bm25", "dpr"):
         for n in (10, 1000):
             assert np.array_equal(od.percentile_distribution(g[f"scores_{s}"], n), g[f"distr_{s}_{n}"])
+
+
+@pytest.mark.parametrize("pooling", ["max", "sum"])
+def test_splade_head_matches_reference(golden_dir, pooling):
+    """oracle/splade_head.py against the verbatim SPLADE.forward / _prune_activations outputs (stub encoder)."""
+    from oracle import splade_head as oh
+    g = _load(golden_dir, "splade_head_small.npz")
+    logits, mask = torch.from_numpy(g["logits"]), torch.from_numpy(g["mask"])
+    act = oh.pool(logits, mask, pooling)
+    assert np.array_equal(act.numpy(), g[f"act_{pooling}"])
+    for k in (1, 32, 517):
+        pruned, idx = oh.prune(act, k)
+        assert np.array_equal(pruned.numpy(), g[f"pruned_{pooling}_{k}"])
+        assert np.array_equal(idx.numpy(), g[f"topk_{pooling}_{k}"])
+    ptr, term, w = oh.to_csr(act)
+    dense = np.zeros_like(g[f"act_{pooling}"])
+    dense[np.repeat(np.arange(len(ptr) - 1), np.diff(ptr)), term] = w
+    assert np.array_equal(dense, g[f"act_{pooling}"]) and ptr[-1] == np.count_nonzero(dense)
+    assert all(np.all(np.diff(term[ptr[i]:ptr[i + 1]]) > 0) for i in range(len(ptr) - 1))
