@@ -31,7 +31,8 @@ extern void* g_debug_stats;
 constexpr int kMsDim = 128;                 // embedding dim (two 64-element swizzle rows)
 constexpr int kMsRows = 128;                // UMMA M: query-token rows per tile
 constexpr int kMsGroupMax = 256;            // doc-token rows per MMA group (UMMA N <= 256)
-constexpr int kMsStages = 3;
+constexpr int kMsStagesDefault = 2;     // doc-group ring depth (FZ_MS_STAGES overrides, 2..8: tuning aid)
+constexpr int kMsStagesMax = 8;
 constexpr int kMsTBufs = 2;                 // 2 x 256 TMEM columns
 constexpr int kMsThreads = 384;             // warps 0-3 control, warps 4-7 and 8-11 two epilogue teams
 constexpr size_t kMsSmemMax = 227 * 1024;
@@ -45,23 +46,31 @@ struct MsArgs {
     const int32_t* count;       // [n_queries] how many of them
     const unsigned char* packed;   // packed token store (fz_maxsim_pack): 256 bytes per packed row
     int n_queries, n_cand, lq;
-    int a_rows;                 // query rows held in shared memory per 64-dim half (lq rounded up to 8)
+    int a_rows;                 // query rows per replica (lq rounded up to 8) = TMA box height
+    int rep;                    // replicas of the query rows in the 128-row A tile (1, 2 or 4)
     int group_rows;             // doc-token rows per stage (multiple of 16, <= 256)
+    int stages;                 // ring depth
     float* out;                 // [n_queries, n_cand], zero-initialised
     unsigned long long* stats;  // optional [gridDim.x, 8] cycle counters (fz_debug_set_stats), NULL = off
 };
 
-// (start row, token count) of every (query, candidate) pair, gathered once by a pre-pass: under a saturated memory
-// system a demand load takes thousands of cycles, so the persistent kernel must not chase cand -> tok_ptr -> tokens
-// pointers on its critical path.  len -1 = candidate outside this shard.
-// One warp per query: the candidates this shard owns, compacted in candidate order, as (first packed row, token count,
-// candidate index, 0).  A shard of a G-way sharded store owns 1/G of them: the persistent kernel walks only those.
+// Pre-pass, one warp per query.  Under a saturated memory system a demand load takes thousands of cycles, so the
+// persistent kernel must not chase cand -> tok_ptr -> tokens pointers on its critical path, and its four roles (one warp
+// each, all walking the same candidate list) must not spend their issue slots on bookkeeping either.  Phase 1 gathers
+// the candidates this shard owns, compacted in candidate order (a shard of a G-way sharded store owns 1/G of them).
+// Phase 2 packs them greedily into MMA groups of <= cap token rows and records the result per candidate:
+//     x = first packed row, y = token count, z = candidate index | flags << 24, w = first TMEM column of the passage
+// so that the persistent kernel only reads decisions.  A passage longer than one group always starts a group and is cut
+// into pieces that each fill a group of their own; the passage after it starts a new group.
+constexpr int kMsNewGroup = 1;      // the passage opens a new group (the previous one, if any, ends before it)
+constexpr int kMsTeamShift = 1;     // flags bits 1..3: epilogue team that reduces the passage (passages go round-robin)
 __global__ void maxsim_info_kernel(const int32_t* __restrict__ cand, const int64_t* __restrict__ tok_ptr,
                                    const int64_t* __restrict__ pk_ptr, long long n_docs, long long doc_base, int n_queries,
-                                   int n_cand, int4* __restrict__ info, int32_t* __restrict__ count) {
+                                   int n_cand, int cap, int n_teams, int4* __restrict__ info, int32_t* __restrict__ count) {
     const int lane = threadIdx.x & 31;
     const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (q >= n_queries) return;
+    int4* __restrict__ mine = info + (size_t)q * n_cand;
     int n_own = 0;
     for (int c0 = 0; c0 < n_cand; c0 += 32) {
         const int c = c0 + lane;
@@ -71,10 +80,42 @@ __global__ void maxsim_info_kernel(const int32_t* __restrict__ cand, const int64
             if (d >= 0 && d < n_docs) v = make_int4((int)pk_ptr[d], (int)(tok_ptr[d + 1] - tok_ptr[d]), c, 0);
         }
         const unsigned own = __ballot_sync(0xffffffffu, v.y >= 0);
-        if (v.y >= 0) info[(size_t)q * n_cand + n_own + __popc(own & ((1u << lane) - 1))] = v;
+        if (v.y >= 0) mine[n_own + __popc(own & ((1u << lane) - 1))] = v;
         n_own += __popc(own);
     }
     if (lane == 0) count[q] = n_own;
+    __syncwarp();
+    int rows = 0, team = 0;
+    bool force_new = true;
+    for (int c0 = 0; c0 < n_own; c0 += 32) {
+        int4 v = c0 + lane < n_own ? mine[c0 + lane] : make_int4(0, -1, 0, 0);
+        const int nb = min(32, n_own - c0);
+        for (int l = 0; l < nb; ++l) {
+            const int len = __shfl_sync(0xffffffffu, v.y, l);
+            if (len <= 0) continue;
+            int flags = team << kMsTeamShift, col = 0;
+            if (++team == n_teams) team = 0;
+            if (len > cap) {
+                flags |= kMsNewGroup;
+                rows = 0;
+                force_new = true;
+            } else {
+                const int R = (len + 7) & ~7;
+                if (force_new || rows + R > cap) {
+                    flags |= kMsNewGroup;
+                    rows = 0;
+                    force_new = false;
+                }
+                col = rows;
+                rows += R;
+            }
+            if (lane == l) {
+                v.z |= flags << 24;
+                v.w = col;
+            }
+        }
+        if (c0 + lane < n_own) mine[c0 + lane] = v;
+    }
 }
 
 // Packed image of one passage: [half 0: R rows x 128 B][half 1: R rows x 128 B], R = rows rounded up to 8 (zero rows),
@@ -100,18 +141,21 @@ __device__ __forceinline__ int4 ms_cand_info(const MsArgs& M, int q, int c0, int
     return c < n_own ? __ldg(&M.info[(size_t)q * M.n_cand + c]) : make_int4(0, -1, 0, 0);
 }
 
-// Walk query q's candidates and cut them into pieces (<= group_rows tokens) packed greedily into groups.  Every role
-// (producer, MMA issuer, both epilogue teams) runs this same warp-uniform walk, so they agree on the packing without
-// exchanging anything.
-//   on_piece(c, row0, off, Rdoc, n, R, col, first_of_cand, last_of_cand, first_of_group)
+// Walk query q's candidates in the packing the pre-pass decided.  Every role (producer, MMA issuer, both epilogue
+// teams) runs this same warp-uniform walk; the only state it carries is the row count of the open group.
+//   on_piece(c, row0, off, Rdoc, n, R, col, first_of_cand, last_of_cand, first_of_group, team1)
 //                                row0 = first packed row of the passage, off = first token of the piece, Rdoc / R =
-//                                rows of the passage / piece rounded up to 8, col = first TMEM column of the piece
+//                                rows of the passage / piece rounded up to 8, col = first TMEM column of the piece,
+//                                team1 = epilogue team the passage belongs to
 //   on_group_end(rows)           rows = columns of the group (multiple of 8; the MMA rounds up to 16)
 //   on_empty(c)                  candidate with zero tokens
 template <class FP, class FG, class FE>
 __device__ __forceinline__ void ms_walk(const MsArgs& M, int q, int lane, FP on_piece, FG on_group_end, FE on_empty) {
     int rows = 0;
     const int n_own = __ldg(&M.count[q]);
+    // 8 columns stay free at the end of a group: the epilogue's 16 / 32-column tcgen05.ld may read up to 8 columns
+    // past a piece
+    const int cap = M.group_rows - 8;
     int4 i1 = ms_cand_info(M, q, 0, lane, n_own), i2 = ms_cand_info(M, q, 32, lane, n_own);   // two blocks of 32 in flight
     for (int c0 = 0; c0 < n_own; c0 += 32) {
         const int4 cur = i1;
@@ -121,24 +165,27 @@ __device__ __forceinline__ void ms_walk(const MsArgs& M, int q, int lane, FP on_
         for (int l = 0; l < nb; ++l) {
             const int start = __shfl_sync(0xffffffffu, cur.x, l);
             const int len = __shfl_sync(0xffffffffu, cur.y, l);
-            const int cidx = __shfl_sync(0xffffffffu, cur.z, l);
+            const int zf = __shfl_sync(0xffffffffu, cur.z, l);
+            const int col = __shfl_sync(0xffffffffu, cur.w, l);
+            const int cidx = zf & 0xffffff;
             if (len <= 0) {
                 if (len == 0) on_empty(cidx);
                 continue;
             }
-            // 8 columns stay free at the end of a group: the epilogue's 16 / 32-column tcgen05.ld may read up to 8
-            // columns past a piece
-            const int cap = M.group_rows - 8;
+            const int team1 = (zf >> (24 + kMsTeamShift)) & 7;
+            const bool new_group = (zf >> 24) & kMsNewGroup;
             const int Rdoc = (len + 7) & ~7;
-            for (int off = 0; off < len; off += cap) {
+            const bool is_long = len > cap;             // cut into pieces that are each a group of their own
+            for (int off = 0; off < len; off += cap) {  // one trip unless the passage is longer than a group
                 const int n = min(cap, len - off);
-                const int R = (n + 7) & ~7;
-                if (rows + R > cap) {
+                const int R = is_long ? (n + 7) & ~7 : Rdoc;
+                const int pc = is_long ? 0 : col;
+                if ((new_group || off > 0) && rows > 0) {
                     on_group_end(rows);
                     rows = 0;
                 }
-                on_piece(cidx, start, off, Rdoc, n, R, rows, off == 0, off + n >= len, rows == 0);
-                rows += R;
+                on_piece(cidx, start, off, Rdoc, n, R, pc, off == 0, off + n >= len, rows == 0, team1);
+                rows = pc + R;
             }
         }
     }
@@ -148,23 +195,30 @@ __device__ __forceinline__ void ms_walk(const MsArgs& M, int q, int lane, FP on_
 __global__ void __launch_bounds__(kMsThreads, 1) maxsim_kernel(const __grid_constant__ MsMaps maps, const MsArgs M) {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
-    const int a_half = M.a_rows * 128;                              // bytes of one 64-dim half of the query operand
-    const int a_bytes = (2 * a_half + 1023) & ~1023;
+    const int a_half = kMsRows * 128;                               // bytes of one 64-dim half of the query operand
+    const int a_bytes = 2 * a_half;
     const int b_half = M.group_rows * 128;
     const int b_bytes = 2 * b_half;                                 // multiple of 4096
     unsigned char* smem_a = smem;                                   // 2 query buffers
-    unsigned char* smem_b = smem + 2 * (size_t)a_bytes;             // kMsStages doc-group stages
+    unsigned char* smem_b = smem + 2 * (size_t)a_bytes;             // M.stages doc-group stages
+    const int kMsStages = M.stages;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + (size_t)kMsStages * b_bytes);
-    uint64_t* full_bar = bars;                          // [kMsStages]
-    uint64_t* empty_bar = full_bar + kMsStages;         // [kMsStages]
-    uint64_t* afull_bar = empty_bar + kMsStages;        // [2]
+    uint64_t* full_bar = bars;                          // [kMsStagesMax]
+    uint64_t* empty_bar = full_bar + kMsStagesMax;      // [kMsStagesMax]
+    uint64_t* afull_bar = empty_bar + kMsStagesMax;     // [2]
     uint64_t* aempty_bar = afull_bar + 2;               // [2]
     uint64_t* tfull_bar = aempty_bar + 2;               // [kMsTBufs]
     uint64_t* tempty_bar = tfull_bar + kMsTBufs;        // [kMsTBufs]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + kMsTBufs);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int live_warps = (M.lq + 31) >> 5;            // epilogue warps per team that own query rows
+    // The UMMA computes 128 query rows whatever lq is.  A query of <= 64 (<= 32) tokens is therefore loaded 2 (4) times
+    // into the A tile: the replicas' accumulator rows hold the same scores in different TMEM lane quarters, and every
+    // replica gets epilogue teams of its own - all eight epilogue warps reduce passages, not just those of the first
+    // lane quarters.
+    const int rep = M.rep;                              // 1, 2 or 4 replicas of the query rows
+    const int wpt = 4 / rep;                            // epilogue warps (TMEM lane quarters) per team
+    const int live_per_team = min(wpt, (M.lq + 31) >> 5);
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&maps.q);
@@ -172,8 +226,8 @@ __global__ void __launch_bounds__(kMsThreads, 1) maxsim_kernel(const __grid_cons
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < kMsStages; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 1); }
         for (int i = 0; i < 2; ++i) { ptx::mbar_init(&afull_bar[i], 1); ptx::mbar_init(&aempty_bar[i], 1); }
-        // both teams pass every accumulator (the owner after reading it), so a waiter can never fall a phase behind
-        for (int i = 0; i < kMsTBufs; ++i) { ptx::mbar_init(&tfull_bar[i], 1); ptx::mbar_init(&tempty_bar[i], 2 * live_warps); }
+        // every team passes every accumulator (the owner after reading it), so a waiter can never fall a phase behind
+        for (int i = 0; i < kMsTBufs; ++i) { ptx::mbar_init(&tfull_bar[i], 1); ptx::mbar_init(&tempty_bar[i], 2 * rep * live_per_team); }
         ptx::fence_barrier_init();
     }
     if (warp == 2) {
@@ -196,13 +250,16 @@ __global__ void __launch_bounds__(kMsThreads, 1) maxsim_kernel(const __grid_cons
             if (lane == 0) {
                 ptx::mbar_wait(&aempty_bar[abuf], ((qi >> 1) & 1) ^ 1);
                 unsigned char* sa = smem_a + (size_t)abuf * a_bytes;
-                ptx::mbar_arrive_expect_tx(&afull_bar[abuf], 2 * a_half);
-                ptx::tma_load_2d(sa, &maps.q, &afull_bar[abuf], 0, q * M.lq);
-                ptx::tma_load_2d(sa + a_half, &maps.q, &afull_bar[abuf], 64, q * M.lq);
+                ptx::mbar_arrive_expect_tx(&afull_bar[abuf], 2 * rep * M.a_rows * 128);
+                for (int r = 0; r < rep; ++r) {
+                    unsigned char* dst = sa + (size_t)r * (kMsRows / rep) * 128;        // replica r: rows r * 128 / rep ...
+                    ptx::tma_load_2d(dst, &maps.q, &afull_bar[abuf], 0, q * M.lq);
+                    ptx::tma_load_2d(dst + a_half, &maps.q, &afull_bar[abuf], 64, q * M.lq);
+                }
             }
             __syncwarp();
             ms_walk(M, q, lane,
-                [&](int, int row0, int off, int Rdoc, int, int R, int col, bool, bool, bool first_of_group) {
+                [&](int, int row0, int off, int Rdoc, int, int R, int col, bool, bool, bool first_of_group, int) {
                     if (lane == 0) {
                         if (first_of_group) {
                             const long long t0 = FZ_CLOCK();
@@ -241,7 +298,7 @@ __global__ void __launch_bounds__(kMsThreads, 1) maxsim_kernel(const __grid_cons
             __syncwarp();
             const uint32_t sa = ptx::smem_u32(smem_a + (size_t)abuf * a_bytes);
             ms_walk(M, q, lane,
-                [&](int, int, int, int, int, int, int, bool, bool, bool) {},
+                [&](int, int, int, int, int, int, int, bool, bool, bool, int) {},
                 [&](int rows) {
                     if (lane == 0) {
                         const uint32_t tb = g % kMsTBufs;
@@ -282,21 +339,21 @@ __global__ void __launch_bounds__(kMsThreads, 1) maxsim_kernel(const __grid_cons
         }
     } else if (warp >= 4) {
         // ===================================== epilogue ==========================================
-        // Two teams of four warps (TMEM lane quarter = warp % 4) take alternate groups, so the TMEM read-back and the
-        // max/sum reduction of one group overlap the next group's.  A passage longer than one group keeps its team.
-        const int team = (warp - 4) >> 2;
-        const int ew = (warp - 4) & 3;
-        if (ew < live_warps) {
-            const int row = ew * 32 + lane;                 // query token handled by this thread
+        // 2 * rep teams (TMEM lane quarter = warp % 4; a team = the wpt quarters of one replica, in one of the two warp
+        // sets 4-7 / 8-11) take the passages round-robin, so the TMEM read-back and the max/sum reduction of one passage
+        // overlap the others'.  A passage longer than one group keeps its team.
+        const int ew = (warp - 4) & 3;                      // TMEM lane quarter
+        const int team = ((warp - 4) >> 2) * rep + ew / wpt;
+        if (ew % wpt < live_per_team) {
+            const int row = (ew % wpt) * 32 + lane;         // query token handled by this thread
             const bool row_ok = row < M.lq;
             uint32_t g = 0;
-            int owner = 0;
             float m = -std::numeric_limits<float>::infinity();
             long long st_wait_tfull = 0, st_tmem = 0, st_sum = 0;
             const long long st_begin = FZ_CLOCK();
             for (int q = blockIdx.x; q < M.n_queries; q += gridDim.x) {
                 ms_walk(M, q, lane,
-                    [&](int c, int, int, int, int n, int, int col, bool first_of_cand, bool last_of_cand, bool first_of_group) {
+                    [&](int c, int, int, int, int n, int, int col, bool, bool last_of_cand, bool first_of_group, int team1) {
                         const uint32_t tb = g % kMsTBufs;
                         if (first_of_group) {
                             const long long t0 = FZ_CLOCK();
@@ -304,8 +361,7 @@ __global__ void __launch_bounds__(kMsThreads, 1) maxsim_kernel(const __grid_cons
                             st_wait_tfull += FZ_CLOCK() - t0;
                             ptx::tc_fence_after();
                         }
-                        if (first_of_cand) owner ^= 1;          // passages alternate between the teams; a continuation
-                        if (owner != team) return;              // piece stays with the team that holds its running max
+                        if (team1 != team) return;              // passages go round-robin over the teams (pre-pass)
                         const long long tq0 = FZ_CLOCK();
                         const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + tb * kMsGroupMax + (uint32_t)col;
                         // 96 columns per step (a whole passage, usually): every tcgen05.ld in flight before the one wait,
@@ -363,11 +419,11 @@ __global__ void __launch_bounds__(kMsThreads, 1) maxsim_kernel(const __grid_cons
                     },
                     [&](int c) {
                         // every (padded) doc token is masked to -9999: max = -9999 for each of the lq query tokens
-                        if (team == 0 && ew == 0 && lane == 0) atomicAdd(&M.out[(size_t)q * M.n_cand + c], -9999.f * (float)M.lq);
+                        if (warp == 4 && lane == 0) atomicAdd(&M.out[(size_t)q * M.n_cand + c], -9999.f * (float)M.lq);
                     });
             }
-            if (M.stats && ew == 0 && lane == 0) {
-                if (team == 0) {
+            if (M.stats && lane == 0) {
+                if (warp == 4) {
                     M.stats[blockIdx.x * 8 + 4] = (unsigned long long)st_wait_tfull;
                     M.stats[blockIdx.x * 8 + 5] = (unsigned long long)(FZ_CLOCK() - st_begin);
                     M.stats[blockIdx.x * 8 + 6] = (unsigned long long)st_tmem;
@@ -414,18 +470,12 @@ extern "C" int fz_maxsim_bf16(const void* q_tok, int lq, const int32_t* cand_ids
     FZ_REQUIRE(((uintptr_t)packed & 1023) == 0, "the packed token store must be 1024-byte aligned");
     FZ_REQUIRE(ws && ws_bytes >= fz_maxsim_workspace_bytes(n_queries, n_cand) && ((uintptr_t)ws & 15) == 0, "workspace too small");
     FZ_REQUIRE(lq >= 1 && lq <= kMsRows, "lq=%d must be in [1,%d]", lq, kMsRows);
-    FZ_REQUIRE(n_docs >= 1 && n_cand >= 1, "bad sizes");
+    FZ_REQUIRE(n_docs >= 1 && n_cand >= 1 && n_cand < (1 << 24), "bad sizes");
     if (n_queries == 0) return FZ_OK;
     FZ_REQUIRE((long long)n_queries * lq < (1ll << 31), "too many query tokens");
 
     int4* info = (int4*)ws;
     int32_t* count = (int32_t*)((char*)ws + (size_t)n_queries * n_cand * sizeof(int4));
-    {
-        ProfScope prof("maxsim_info", stream);
-        maxsim_info_kernel<<<ceil_div(n_queries, 8), 256, 0, stream>>>(cand_ids, tok_ptr, pk_ptr, n_docs, doc_base, n_queries,
-                                                                       n_cand, info, count);
-        FZ_LAUNCH_CHECK();
-    }
     MsArgs M;
     M.info = info;
     M.count = count;
@@ -438,13 +488,28 @@ extern "C" int fz_maxsim_bf16(const void* q_tok, int lq, const int32_t* cand_ids
     M.stats = (unsigned long long*)g_debug_stats;
     // shared memory: 2 query buffers + kMsStages doc groups + barriers; the UMMA reads 128 query rows per half, so the
     // 64 KB it may touch past a short query buffer must still be inside the allocation (the stages follow it)
-    const size_t a_bytes = ((size_t)2 * M.a_rows * 128 + 1023) & ~(size_t)1023;
+    M.rep = lq <= 32 ? 4 : (lq <= 64 ? 2 : 1);
+    const size_t a_bytes = (size_t)2 * kMsRows * 128;
     const size_t fixed = 1024 /*align*/ + 2 * a_bytes + 256 /*barriers*/;
+    static int stages_env = -1;
+    if (stages_env < 0) {
+        const char* e = getenv("FZ_MS_STAGES");
+        stages_env = e ? atoi(e) : kMsStagesDefault;
+        if (stages_env < 2 || stages_env > kMsStagesMax) stages_env = kMsStagesDefault;
+    }
+    const int kMsStages = stages_env;
+    M.stages = kMsStages;
     int group_rows = (int)((kMsSmemMax - fixed) / kMsStages / 256) & ~15;
     if (group_rows > kMsGroupMax) group_rows = kMsGroupMax;
     M.group_rows = group_rows;
     const size_t smem = fixed + (size_t)kMsStages * group_rows * 256;
     FZ_REQUIRE(group_rows >= 64 && smem <= kMsSmemMax, "shared memory plan failed (lq=%d)", lq);
+    {
+        ProfScope prof("maxsim_info", stream);
+        maxsim_info_kernel<<<ceil_div(n_queries, 8), 256, 0, stream>>>(cand_ids, tok_ptr, pk_ptr, n_docs, doc_base, n_queries,
+                                                                       n_cand, group_rows - 8, 2 * M.rep, info, count);
+        FZ_LAUNCH_CHECK();
+    }
 
     MsMaps maps;
     int rc = make_bf16_tile_map(&maps.q, q_tok, (uint64_t)n_queries * lq, kMsDim, (uint32_t)M.a_rows);

@@ -90,14 +90,9 @@ class HybridSearcher:
         """-> {system: (scores [Qs, k], ids int32 [Qs, k])} for this rank's query slice, best first."""
         out = {}
         self._events = []
-        if self.lexical is not None:
-            s, i = self._timed("bm25", lambda: ops.sparse_topk(self.lexical.view(), q.lex_ptr, q.lex_term, None, self.k,
-                                                                self.lexical.doc_base))
-            out["bm25"] = self._timed("bm25_merge", lambda: self._merge(s, i))
-        if self.sparse is not None:
-            s, i = self._timed("splade", lambda: ops.sparse_topk(self.sparse.view(), q.sp_ptr, q.sp_term, q.sp_weight,
-                                                                  self.k, self.sparse.doc_base))
-            out["splade"] = self._timed("splade_merge", lambda: self._merge(s, i))
+        # Execution order: the tensor-core GEMM first, MaxSim (which rescoring needs its list) last, so that the
+        # HBM-bound MaxSim stream does not start under the GEMM's power cap; the returned dict keeps the system order
+        # bm25, splade, dpr, colbert (fusion breaks ties by first insertion, hybrid.py:294-307).
         if self.dense is not None:
             def run_dense():
                 q32, q16 = self.dense.prepare_queries(q.dense)
@@ -110,9 +105,17 @@ class HybridSearcher:
                                       tau_reduce=reduce, n_shards=self.world)
             s, i = self._timed("dpr", run_dense)
             out["dpr"] = self._timed("dpr_merge", lambda: self._merge(s, i))
+        if self.lexical is not None:
+            s, i = self._timed("bm25", lambda: ops.sparse_topk(self.lexical.view(), q.lex_ptr, q.lex_term, None, self.k,
+                                                                self.lexical.doc_base))
+            out["bm25"] = self._timed("bm25_merge", lambda: self._merge(s, i))
+        if self.sparse is not None:
+            s, i = self._timed("splade", lambda: ops.sparse_topk(self.sparse.view(), q.sp_ptr, q.sp_term, q.sp_weight,
+                                                                  self.k, self.sparse.doc_base))
+            out["splade"] = self._timed("splade_merge", lambda: self._merge(s, i))
         if self.tokens is not None:
             out["colbert"] = self._timed("colbert", lambda: self._colbert(q, out))
-        return out
+        return {name: out[name] for name in ("bm25", "splade", "dpr", "colbert") if name in out}
 
     def _colbert(self, q: HybridQueries, lists):
         """MaxSim-rescore the first available system's merged top-k candidates (north-star config 4)."""

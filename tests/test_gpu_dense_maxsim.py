@@ -83,14 +83,16 @@ def test_dense_topk_bf16_mode_overlap():
     assert hit / tot >= 0.999
 
 
-@pytest.mark.parametrize("lq,n_cand", [(64, 40), (32, 33), (128, 7)])
-def test_maxsim_vs_oracle(lq, n_cand):
-    """Doc lengths 1..300 (chunking beyond 128 tokens), candidates outside the shard, an empty document."""
+@pytest.mark.parametrize("lq,n_cand,max_len", [(64, 40, 300), (32, 33, 300), (128, 7, 300), (64, 70, 900), (17, 100, 60)])
+def test_maxsim_vs_oracle(lq, n_cand, max_len):
+    """Doc lengths 1..max_len (passages longer than one MMA group are cut into 2-4 pieces), candidates outside the
+    shard, an empty document, exact multiples of the group capacity."""
     from fusion_b200 import ops
     nq, n_docs = 5, 300
     rng = np.random.Generator(np.random.PCG64(71))
-    lens = rng.integers(1, 301, n_docs)
+    lens = rng.integers(1, max_len + 1, n_docs)
     lens[3] = 0
+    lens[5], lens[6], lens[7] = 248, 496, 249
     ptr = np.zeros(n_docs + 1, dtype=np.int64)
     np.cumsum(lens, out=ptr[1:])
     emb = rng.standard_normal((int(ptr[-1]), 128), dtype=np.float32)
