@@ -17,9 +17,9 @@ struct KeyBits<uint64_t> { static constexpr int hi_bits = 64; };
 
 // hist: 256 counters in shared memory; bcast: 4 ints in shared memory.  All threads of the CTA must call.
 // Requires 1 <= k <= n.  On return (kth_hi, kth_lo) is the k-th largest key.
-// Scores of one query share their sign and exponent bits, so whole passes fall into ONE bin: the histogram is
-// aggregated per warp (__match_any_sync) before it touches shared memory, and the passes stop as soon as the k-th
-// key's bin holds a single key (normally once the score bits are consumed - the doc-id bits only break exact ties).
+// Scores of one query share their sign and exponent bits, so whole passes fall into ONE bin: a warp whose keys share
+// the digit adds its count with one atomic, and the passes stop as soon as the k-th key's bin holds a single key
+// (normally once the score bits are consumed - the doc-id bits only break exact ties).
 template <typename HiT, typename GetHi, typename GetLo>
 __device__ void cta_radix_select_kth_by(GetHi get_hi, GetLo get_lo, int n, int k, int* hist, int* bcast, HiT& kth_hi,
                                         uint32_t& kth_lo) {
@@ -42,10 +42,19 @@ __device__ void cta_radix_select_kth_by(GetHi get_hi, GetLo get_lo, int n, int k
                 match = (h & m_hi) == p_hi && (l & m_lo) == p_lo;
                 d = in_hi ? (uint32_t)(h >> (shift - 32)) & 255u : (l >> shift) & 255u;
             }
+            // One shared-memory atomic per warp when all matching lanes share the digit (whole passes do: the scores of
+            // one query share sign and exponent), plain atomics on the spread-out digits otherwise.  (__match_any_sync
+            // would aggregate every case but costs far more than the conflicts it saves.)
             const unsigned act = __ballot_sync(0xffffffffu, match);
-            if (match) {
-                const unsigned peers = __match_any_sync(act, d);
-                if (lane == __ffs(peers) - 1) atomicAdd(&hist[d], __popc(peers));
+            if (act) {
+                const int leader = __ffs(act) - 1;
+                const uint32_t d0 = __shfl_sync(0xffffffffu, d, leader);
+                const bool uniform = __all_sync(0xffffffffu, !match || d == d0);
+                if (uniform) {
+                    if (lane == leader) atomicAdd(&hist[d0], __popc(act));
+                } else if (match) {
+                    atomicAdd(&hist[d], 1);
+                }
             }
         }
         __syncthreads();

@@ -90,9 +90,10 @@ class HybridSearcher:
         """-> {system: (scores [Qs, k], ids int32 [Qs, k])} for this rank's query slice, best first."""
         out = {}
         self._events = []
-        # Execution order: the tensor-core GEMM first, MaxSim (which rescoring needs its list) last, so that the
-        # HBM-bound MaxSim stream does not start under the GEMM's power cap; the returned dict keeps the system order
-        # bm25, splade, dpr, colbert (fusion breaks ties by first insertion, hybrid.py:294-307).
+        # Execution order: the tensor-core GEMM first, then SPLADE, BM25 and MaxSim (which needs the GEMM's list) last:
+        # the kernel that follows the GEMM starts under its power cap, and SPLADE's is the one with the most headroom.
+        # The returned dict keeps the system order bm25, splade, dpr, colbert (fusion breaks ties by first insertion,
+        # hybrid.py:294-307).
         if self.dense is not None:
             def run_dense():
                 q32, q16 = self.dense.prepare_queries(q.dense)
@@ -105,21 +106,21 @@ class HybridSearcher:
                                       tau_reduce=reduce, n_shards=self.world)
             s, i = self._timed("dpr", run_dense)
             out["dpr"] = self._timed("dpr_merge", lambda: self._merge(s, i))
-        if self.lexical is not None:
-            s, i = self._timed("bm25", lambda: ops.sparse_topk(self.lexical.view(), q.lex_ptr, q.lex_term, None, self.k,
-                                                                self.lexical.doc_base))
-            out["bm25"] = self._timed("bm25_merge", lambda: self._merge(s, i))
         if self.sparse is not None:
             s, i = self._timed("splade", lambda: ops.sparse_topk(self.sparse.view(), q.sp_ptr, q.sp_term, q.sp_weight,
                                                                   self.k, self.sparse.doc_base))
             out["splade"] = self._timed("splade_merge", lambda: self._merge(s, i))
+        if self.lexical is not None:
+            s, i = self._timed("bm25", lambda: ops.sparse_topk(self.lexical.view(), q.lex_ptr, q.lex_term, None, self.k,
+                                                                self.lexical.doc_base))
+            out["bm25"] = self._timed("bm25_merge", lambda: self._merge(s, i))
         if self.tokens is not None:
             out["colbert"] = self._timed("colbert", lambda: self._colbert(q, out))
         return {name: out[name] for name in ("bm25", "splade", "dpr", "colbert") if name in out}
 
     def _colbert(self, q: HybridQueries, lists):
         """MaxSim-rescore the first available system's merged top-k candidates (north-star config 4)."""
-        src = "dpr" if "dpr" in lists else next(iter(lists))
+        src = next(n for n in ("dpr", "bm25", "splade") if n in lists)
         cand = lists[src][1]                                            # [Qs, k] global ids of this rank's query slice
         cand_all = sharding.allgather_rows(cand, self.group)[: q.colbert.shape[0]] if self.world > 1 else cand
         pool_ids = cand_all if self.colbert_pool is None else torch.where(cand_all >= 0, cand_all % self.colbert_pool, cand_all)
