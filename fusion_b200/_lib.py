@@ -30,6 +30,15 @@ class Postings(C.Structure):
                 ("tile_docs", C.c_int32), ("n_tiles", C.c_int32), ("n_coarse", C.c_int32), ("n_docs", C.c_int64)]
 
 
+SHARD_HOOK = C.CFUNCTYPE(C.c_int, C.c_void_p)      # fz_shard_hook_t
+
+
+class ShardSync(C.Structure):
+    """mirror of fz_shard_sync_t"""
+    _fields_ = [("hook", SHARD_HOOK), ("user", C.c_void_p), ("exchange", C.c_void_p), ("n_shards", C.c_int32),
+                ("sched_docs", C.c_int64)]
+
+
 _p, _i, _i64, _sz, _f, _d = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_float, C.c_double
 
 # name -> (restype, argtypes); must list every symbol of include/fusion_b200.h (tests/test_abi.py checks)
@@ -58,13 +67,13 @@ SIGNATURES = {
     "fz_csr_fill": (_i, [_p, _i, _i, _p, _p, _p, _p]),
     "fz_lexical_impacts": (_i, [_p, _p, _p, _p, _p, C.c_int32, _i64, _d, _d, _d, _i, _p, _p]),
     "fz_sparse_topk_workspace_bytes": (_sz, [_i, _i, _i, _i]),
-    "fz_sparse_topk_f64": (_i, [_p, _p, _p, _i, _i, _i64, _i, _i, _i, _p, _p, _p, _p, _sz, _p]),
-    "fz_sparse_topk_f32": (_i, [_p, _p, _p, _p, _i, _i, _i64, _i, _i, _i, _p, _p, _p, _p, _sz, _p]),
+    "fz_sparse_topk_f64": (_i, [_p, _p, _p, _i, _i, _i64, _i, _i, _i, _p, _p, _p, _p, _sz, _p, _p]),
+    "fz_sparse_topk_f32": (_i, [_p, _p, _p, _p, _i, _i, _i64, _i, _i, _i, _p, _p, _p, _p, _sz, _p, _p]),
     "fz_sparse_scores_f64": (_i, [_p, _p, _p, _i, _p, _p]),
     "fz_sparse_scores_f32": (_i, [_p, _p, _p, _p, _i, _p, _p]),
     "fz_dense_topk_workspace_bytes": (_sz, [_i, _i, _i]),
     "fz_dense_topk": (_i, [_p, _p, _p, _p, _i, _i64, _i, _i, _f, _i64, _i, _i, _p, _p, _p, _p, _sz, _p]),
-    "fz_dense_topk_filter": (_i, [_p, _p, _i, _i64, _i, _i, _f, _i64, _i, _i, _i, _p, _p, _p, _sz, _p]),
+    "fz_dense_topk_filter": (_i, [_p, _p, _i, _i64, _i, _i, _f, _i64, _i, _i, _i, _p, _p, _p, _sz, _p, _p]),
     "fz_dense_topk_finish": (_i, [_p, _p, _p, _i, _i, _i, _i64, _i, _p, _p, _p, _p, _sz, _p]),
     "fz_dense_scores_f32": (_i, [_p, _p, _i, _i64, _i, _p, _p]),
     "fz_normalize_rows": (_i, [_p, _i64, _i, _i, _p, _p, _p]),

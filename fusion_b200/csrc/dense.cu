@@ -418,7 +418,8 @@ size_t fz_dense_topk_workspace_bytes(int n_queries, int k, int cap) {
 
 static int dense_filter_phase(const void* q_bf16, const void* d_bf16, bool exact, int n_queries, int64_t n_docs, int dim,
                               int k, float margin, int64_t doc_base, int cap, int growth, float* out_scores,
-                              int32_t* out_ids, int32_t* out_status, void* ws, cudaStream_t stream) {
+                              int32_t* out_ids, int32_t* out_status, void* ws, const fz_shard_sync_t* sync,
+                              cudaStream_t stream) {
     CUtensorMap tmap_q, tmap_d;
     int rc = make_bf16_tile_map(&tmap_q, q_bf16, (uint64_t)n_queries, (uint64_t)dim, kBM);
     if (rc) return rc;
@@ -438,26 +439,31 @@ static int dense_filter_phase(const void* q_bf16, const void* d_bf16, bool exact
     G.stats = (unsigned long long*)g_debug_stats;
     rc = cand_init<float>(G.st, n_queries, stream);
     if (rc) return rc;
-    long long lo = 0, hi = n_docs < cap ? n_docs : cap;
+    const bool synced = sync && sync->hook;
+    FZ_REQUIRE(!synced || (sync->exchange && sync->n_shards >= 1 && sync->sched_docs >= n_docs), "bad shard sync");
+    const long long SN = synced ? (long long)sync->sched_docs : n_docs;     // the schedule every shard follows
+    long long lo = 0, hi = SN < cap ? SN : cap;
     while (true) {
-        G.r_lo = lo;
-        G.r_hi = hi;
-        G.n_tiles = (int)ceil_div<long long>(hi - lo, kBN);
-        const long long pair_tiles = (long long)ceil_div(G.m_tiles, kPair) * G.n_tiles;
-        const int max_clusters = num_sms() / kPair;
-        const int grid = kPair * (int)(pair_tiles < max_clusters ? pair_tiles : max_clusters);
-        {
+        G.r_lo = lo < n_docs ? lo : n_docs;
+        G.r_hi = hi < n_docs ? hi : n_docs;
+        if (G.r_hi > G.r_lo) {
+            G.n_tiles = (int)ceil_div<long long>(G.r_hi - G.r_lo, kBN);
+            const long long pair_tiles = (long long)ceil_div(G.m_tiles, kPair) * G.n_tiles;
+            const int max_clusters = num_sms() / kPair;
+            const int grid = kPair * (int)(pair_tiles < max_clusters ? pair_tiles : max_clusters);
             ProfScope prof("dense_filter_gemm", stream);
             dense_filter_kernel<<<grid, kGemmThreads, kGemmSmem, stream>>>(tmap_q, tmap_d, G);
         }
         FZ_LAUNCH_CHECK();
-        const bool last = hi >= n_docs;
-        rc = cand_select<float>(G.st, n_queries, k, margin, last && !exact, doc_base, out_scores, out_ids, nullptr, stream);
+        const bool last = hi >= SN;
+        const float* floor = last ? nullptr : shard_floor<float>(sync, G.st, n_queries, k, margin, stream, &rc);
+        if (rc) return rc;
+        rc = cand_select<float>(G.st, n_queries, k, margin, last && !exact, doc_base, out_scores, out_ids, nullptr, stream, floor);
         if (rc) return rc;
         if (last) break;
         lo = hi;
         hi = growth >= 2 ? hi * growth : hi + (cap - k);
-        if (hi > n_docs) hi = n_docs;
+        if (hi > SN) hi = SN;
     }
     return FZ_OK;
 }
@@ -499,14 +505,14 @@ int fz_dense_topk(const void* q_bf16, const void* d_bf16, const float* q_f32, co
     if (n_queries == 0) return FZ_OK;
     const bool exact = d_f32 != nullptr;
     rc = dense_filter_phase(q_bf16, d_bf16, exact, n_queries, n_docs, dim, k, margin, doc_base, cap, growth, out_scores,
-                            out_ids, out_status, ws, stream);
+                            out_ids, out_status, ws, nullptr, stream);
     if (rc || !exact) return rc;
     return dense_finish_phase(q_f32, d_f32, nullptr, n_queries, dim, k, doc_base, cap, out_scores, out_ids, out_status, ws, stream);
 }
 
 int fz_dense_topk_filter(const void* q_bf16, const void* d_bf16, int n_queries, int64_t n_docs, int dim, int k, float margin,
                          int64_t doc_base, int cap, int growth, int floor_rank, float* out_tau, int32_t* out_status, void* ws,
-                         size_t ws_bytes, fz_stream_t stream_) {
+                         size_t ws_bytes, const fz_shard_sync_t* sync, fz_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     FZ_REQUIRE(out_tau, "null pointer");
     int rc = dense_check(q_bf16, d_bf16, nullptr, nullptr, n_queries, n_docs, dim, k, margin, cap, growth, out_tau,
@@ -514,11 +520,11 @@ int fz_dense_topk_filter(const void* q_bf16, const void* d_bf16, int n_queries, 
     if (rc) return rc;
     if (n_queries == 0) return FZ_OK;
     rc = dense_filter_phase(q_bf16, d_bf16, true, n_queries, n_docs, dim, k, margin, doc_base, cap, growth, nullptr, nullptr,
-                            out_status, ws, stream);
+                            out_status, ws, sync, stream);
     if (rc) return rc;
     FZ_REQUIRE(floor_rank >= 1 && floor_rank <= k, "floor_rank=%d must be in [1, k]", floor_rank);
     const CandState<float> st = cand_state_carve<float>(ws, n_queries, cap, out_status);
-    return cand_kth_score(st, n_queries, floor_rank, margin, out_tau, stream);
+    return cand_kth_score<float>(st, n_queries, floor_rank, margin, out_tau, stream);
 }
 
 int fz_dense_topk_finish(const float* q_f32, const float* d_f32, const float* tau_floor, int n_queries, int dim, int k,

@@ -151,7 +151,8 @@ __device__ __forceinline__ void hi_score(uint64_t h, double& s) { s = unord64(h)
 template <typename ST>
 __global__ void __launch_bounds__(SelectCfg<ST>::threads, SelectCfg<ST>::blocks) cand_select_kernel(CandState<ST> st, int k, ST margin, int final_out,
                                                                    long long doc_base, ST* out_scores,
-                                                                   int32_t* out_ids, int32_t* out_n, int k_pow2) {
+                                                                   int32_t* out_ids, int32_t* out_n, int k_pow2,
+                                                                   const ST* __restrict__ floor) {
     using HiT = typename HiOf<ST>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     HiT* s_hi = reinterpret_cast<HiT*>(smem_raw);                               // [cap]
@@ -187,6 +188,20 @@ __global__ void __launch_bounds__(SelectCfg<ST>::threads, SelectCfg<ST>::blocks)
         const ST t = kth - margin;
         if (t > tau) tau = t;
     }
+    // Cross-shard floor (sharded corpus): a score f such that at least k documents over ALL shards reach it.  Records
+    // below f can never enter the global top-k; records that TIE f must stay (the doc that ties may have a lower id than
+    // the k counted ones, which live on other shards), so the stored threshold is the next value below f: the scoring
+    // kernels emit score > tau.
+    HiT floor_hi = 0;
+    if (floor) {
+        const ST f = floor[q];
+        if (f > -std::numeric_limits<ST>::infinity()) {
+            floor_hi = (HiT)score_key(f);
+            ST below;
+            hi_score((HiT)(floor_hi - 1), below);
+            if (below > tau) tau = below;
+        }
+    }
     // survivors: exactly the k best when margin == 0 (a later doc that only ties the k-th score loses the tie:
     // rounds visit docs in ascending id order), everything with score >= tau otherwise; all records if n < k
     const HiT tau_hi = (HiT)score_key(tau);
@@ -201,7 +216,7 @@ __global__ void __launch_bounds__(SelectCfg<ST>::threads, SelectCfg<ST>::blocks)
             h = s_hi[i];
             l = s_lo[i];
             win = !full || key_ge<HiT>(h, l, kth_hi, kth_lo);
-            keep = !full || (margin == (ST)0 ? win : h >= tau_hi);
+            keep = (!full || (margin == (ST)0 ? win : h >= tau_hi)) && h >= floor_hi;
         }
         const unsigned bk = __ballot_sync(0xffffffffu, keep);
         const unsigned bw = __ballot_sync(0xffffffffu, final_out && win);
@@ -256,40 +271,54 @@ __global__ void __launch_bounds__(SelectCfg<ST>::threads, SelectCfg<ST>::blocks)
 }
 
 // out[q] = (rank-th best score in query q's candidate buffer) - margin, or -inf when it holds fewer than `rank` records;
-// the buffer is left untouched (the cross-shard rescoring floor of the exact dense mode)
-__global__ void __launch_bounds__(512) cand_kth_kernel(CandState<float> st, int rank, float margin, float* __restrict__ out) {
+// the buffer is left untouched (cross-shard thresholds: every shard holds >= rank records at or above its value, so the
+// minimum over G shards with rank = ceil(k / G) is reached by at least k documents overall)
+template <typename ST>
+__global__ void __launch_bounds__(512) cand_kth_kernel(CandState<ST> st, int rank, ST margin, ST* __restrict__ out) {
+    using HiT = typename HiOf<ST>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint32_t* s_hi = reinterpret_cast<uint32_t*>(smem_raw);
-    uint32_t* s_lo = s_hi + st.cap;
+    HiT* s_hi = reinterpret_cast<HiT*>(smem_raw);
+    uint32_t* s_lo = reinterpret_cast<uint32_t*>(s_hi + st.cap);
     __shared__ int s_hist[256];
     __shared__ int s_bcast[4];
     const int q = blockIdx.x;
     const int n = min(st.cnt[q], st.cap);
     if (n < rank) {
-        if (threadIdx.x == 0) out[q] = -std::numeric_limits<float>::infinity();
+        if (threadIdx.x == 0) out[q] = -std::numeric_limits<ST>::infinity();
         return;
     }
     const size_t off = (size_t)q * st.cap;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        s_hi[i] = (uint32_t)score_key(st.score[off + i]);
+        s_hi[i] = (HiT)score_key(st.score[off + i]);
         s_lo[i] = ~(uint32_t)st.id[off + i];
     }
     __syncthreads();
-    uint32_t kth_hi = 0, kth_lo = 0;
-    cta_radix_select_kth<uint32_t>(s_hi, s_lo, n, rank, s_hist, s_bcast, kth_hi, kth_lo);
-    if (threadIdx.x == 0) out[q] = unord32(kth_hi) - margin;
+    HiT kth_hi = 0;
+    uint32_t kth_lo = 0;
+    cta_radix_select_kth<HiT>(s_hi, s_lo, n, rank, s_hist, s_bcast, kth_hi, kth_lo);
+    if (threadIdx.x == 0) {
+        ST v;
+        hi_score(kth_hi, v);
+        out[q] = v - margin;
+    }
 }
 
-int cand_kth_score(const CandState<float>& st, int n_queries, int rank, float margin, float* out, cudaStream_t stream) {
-    static bool attr = false;
-    if (!attr) {
-        FZ_CUDA(cudaFuncSetAttribute(cand_kth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        attr = true;
+template <typename ST>
+int cand_kth_score(const CandState<ST>& st, int n_queries, int rank, ST margin, ST* out, cudaStream_t stream) {
+    using HiT = typename HiOf<ST>::type;
+    static bool attr_f = false, attr_d = false;
+    bool& done = std::is_same<ST, float>::value ? attr_f : attr_d;
+    if (!done) {
+        FZ_CUDA(cudaFuncSetAttribute(cand_kth_kernel<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        done = true;
     }
-    cand_kth_kernel<<<n_queries, 512, (size_t)st.cap * 8, stream>>>(st, rank, margin, out);
+    ProfScope prof("cand_kth", stream);
+    cand_kth_kernel<ST><<<n_queries, 512, (size_t)st.cap * (sizeof(HiT) + 4), stream>>>(st, rank, margin, out);
     FZ_LAUNCH_CHECK();
     return FZ_OK;
 }
+template int cand_kth_score<float>(const CandState<float>&, int, int, float, float*, cudaStream_t);
+template int cand_kth_score<double>(const CandState<double>&, int, int, double, double*, cudaStream_t);
 
 template <typename ST>
 int cand_init(const CandState<ST>& st, int n_queries, cudaStream_t stream) {
@@ -300,7 +329,7 @@ int cand_init(const CandState<ST>& st, int n_queries, cudaStream_t stream) {
 
 template <typename ST>
 int cand_select(const CandState<ST>& st, int n_queries, int k, ST margin, bool final_out, int64_t doc_base,
-                ST* out_scores, int32_t* out_ids, int32_t* out_n, cudaStream_t stream) {
+                ST* out_scores, int32_t* out_ids, int32_t* out_n, cudaStream_t stream, const ST* floor) {
     FZ_REQUIRE(st.cap <= kSmemEntries, "candidate capacity %d exceeds %d", st.cap, kSmemEntries);
     FZ_REQUIRE(k >= 1 && k <= st.cap, "k=%d must be in [1, cap=%d]", k, st.cap);
     using HiT = typename HiOf<ST>::type;
@@ -318,7 +347,7 @@ int cand_select(const CandState<ST>& st, int n_queries, int k, ST margin, bool f
     ProfScope prof(std::is_same<ST, float>::value ? "cand_select_f32" : "cand_select_f64", stream);
     cand_select_kernel<ST><<<n_queries, SelectCfg<ST>::threads, smem, stream>>>(st, k, margin, final_out ? 1 : 0,
                                                                       (long long)doc_base, out_scores, out_ids, out_n,
-                                                                      k_pow2);
+                                                                      k_pow2, floor);
     FZ_LAUNCH_CHECK();
     return FZ_OK;
 }
@@ -326,9 +355,9 @@ int cand_select(const CandState<ST>& st, int n_queries, int k, ST margin, bool f
 template int cand_init<float>(const CandState<float>&, int, cudaStream_t);
 template int cand_init<double>(const CandState<double>&, int, cudaStream_t);
 template int cand_select<float>(const CandState<float>&, int, int, float, bool, int64_t, float*, int32_t*, int32_t*,
-                                cudaStream_t);
+                                cudaStream_t, const float*);
 template int cand_select<double>(const CandState<double>&, int, int, double, bool, int64_t, double*, int32_t*,
-                                 int32_t*, cudaStream_t);
+                                 int32_t*, cudaStream_t, const double*);
 
 // --------------------------------------------------------------------------------- merge / rank rows
 // Segment q gathers `n_src` runs of `run_len` records spaced `src_stride` apart (merge), or one run of

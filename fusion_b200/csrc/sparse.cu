@@ -380,7 +380,9 @@ __global__ void __launch_bounds__(kMaxSparseThreads) sparse_zero_fill_kernel(con
     const int q = blockIdx.x;
     // after the final select cnt[q] is the number of positive-score docs kept: all of them when there are < k
     const int n_have = A.st.cnt[q];
-    if (n_have >= A.k || A.sign_mode < 0) return;           // negatives never need zero fill
+    // negatives never need zero fill; a positive threshold means k positive-score docs exist (on this shard, or - with a
+    // cross-shard floor - over all shards), so no zero-score doc can reach the top-k
+    if (n_have >= A.k || A.sign_mode < 0 || A.st.tau[q] > (AccT)0) return;
     const int need = A.k - n_have;
     const int n_warps = blockDim.x >> 5;
     if (threadIdx.x == 0) {
@@ -473,7 +475,8 @@ static int set_smem_attrs() {
 template <typename AccT>
 static int sparse_topk(const fz_postings_t* ix, const int32_t* q_ptr, const int32_t* q_term, const float* q_weight,
                        int n_queries, int k, int64_t doc_base, int cap, int growth, int sign_mode, AccT* out_scores,
-                       int32_t* out_ids, int32_t* out_status, void* ws, size_t ws_bytes, cudaStream_t stream) {
+                       int32_t* out_ids, int32_t* out_status, void* ws, size_t ws_bytes, const fz_shard_sync_t* sync,
+                       cudaStream_t stream) {
     int rc = check_index<AccT>(ix);
     if (rc) return rc;
     FZ_REQUIRE(q_ptr && q_term && out_scores && out_ids && out_status, "null pointer");
@@ -504,32 +507,37 @@ static int sparse_topk(const fz_postings_t* ix, const int32_t* q_ptr, const int3
     const int threads = sparse_threads<AccT>(ix->tile_docs);
     const size_t smem = sparse_smem<AccT>(ix->tile_docs);
     const long long N = ix->n_docs;
+    const bool synced = sync && sync->hook;
+    FZ_REQUIRE(!synced || (sync->exchange && sync->n_shards >= 1 && sync->sched_docs >= N), "bad shard sync");
+    const long long SN = synced ? (long long)sync->sched_docs : N;     // the schedule every shard follows
     // Rounds end on tile boundaries where that keeps them overflow-free (a tile cut by a boundary is accumulated twice)
     auto align_hi = [&](long long lo, long long hi) {
         const long long a = hi / ix->tile_docs * ix->tile_docs;
         return a > lo ? a : hi;
     };
-    long long lo = 0, hi = N < cap ? N : align_hi(0, cap);
+    long long lo = 0, hi = SN < cap ? SN : align_hi(0, cap);
     while (true) {
-        A.r_lo = lo;
-        A.r_hi = hi;
-        A.tile_lo = (int)(lo / ix->tile_docs);
-        A.tile_hi = (int)ceil_div<long long>(hi, ix->tile_docs);
-        A.group_lo = A.tile_lo / kGroupTiles;
-        const long long blocks = (long long)(ceil_div(A.tile_hi, kGroupTiles) - A.group_lo) * n_queries;
-        FZ_REQUIRE(blocks < (1ll << 31), "grid too large");
-        {
+        A.r_lo = lo < N ? lo : N;
+        A.r_hi = hi < N ? hi : N;
+        if (A.r_hi > A.r_lo) {
+            A.tile_lo = (int)(A.r_lo / ix->tile_docs);
+            A.tile_hi = (int)ceil_div<long long>(A.r_hi, ix->tile_docs);
+            A.group_lo = A.tile_lo / kGroupTiles;
+            const long long blocks = (long long)(ceil_div(A.tile_hi, kGroupTiles) - A.group_lo) * n_queries;
+            FZ_REQUIRE(blocks < (1ll << 31), "grid too large");
             ProfScope prof(sizeof(AccT) == 8 ? "sparse_tile_f64" : "sparse_tile_f32", stream);
             sparse_tile_kernel<AccT, 0><<<(unsigned)blocks, threads, smem, stream>>>(A);
         }
         FZ_LAUNCH_CHECK();
-        const bool last = hi >= N;
-        rc = cand_select<AccT>(A.st, n_queries, k, (AccT)0, last, doc_base, out_scores, out_ids, nullptr, stream);
+        const bool last = hi >= SN;
+        const AccT* floor = last ? nullptr : shard_floor<AccT>(sync, A.st, n_queries, k, (AccT)0, stream, &rc);
+        if (rc) return rc;
+        rc = cand_select<AccT>(A.st, n_queries, k, (AccT)0, last, doc_base, out_scores, out_ids, nullptr, stream, floor);
         if (rc) return rc;
         if (last) break;
         lo = hi;
         hi = growth >= 2 ? hi * growth : hi + (cap - k);
-        if (hi >= N) hi = N; else hi = align_hi(lo, hi);
+        if (hi >= SN) hi = SN; else hi = align_hi(lo, hi);
     }
     ProfScope prof("sparse_zero_fill", stream);
     sparse_zero_fill_kernel<AccT><<<n_queries, threads, smem, stream>>>(A);
@@ -591,16 +599,17 @@ size_t fz_sparse_topk_workspace_bytes(int n_queries, int k, int cap, int is_f64)
 
 int fz_sparse_topk_f64(const fz_postings_t* index, const int32_t* q_ptr, const int32_t* q_term, int n_queries, int k,
                        int64_t doc_base, int cap, int growth, int sign_mode, double* out_scores, int32_t* out_ids,
-                       int32_t* out_status, void* ws, size_t ws_bytes, fz_stream_t stream) {
+                       int32_t* out_status, void* ws, size_t ws_bytes, const fz_shard_sync_t* sync, fz_stream_t stream) {
     return sparse_topk<double>(index, q_ptr, q_term, nullptr, n_queries, k, doc_base, cap, growth, sign_mode,
-                               out_scores, out_ids, out_status, ws, ws_bytes, (cudaStream_t)stream);
+                               out_scores, out_ids, out_status, ws, ws_bytes, sync, (cudaStream_t)stream);
 }
 
 int fz_sparse_topk_f32(const fz_postings_t* index, const int32_t* q_ptr, const int32_t* q_term, const float* q_weight,
                        int n_queries, int k, int64_t doc_base, int cap, int growth, int sign_mode, float* out_scores,
-                       int32_t* out_ids, int32_t* out_status, void* ws, size_t ws_bytes, fz_stream_t stream) {
+                       int32_t* out_ids, int32_t* out_status, void* ws, size_t ws_bytes, const fz_shard_sync_t* sync,
+                       fz_stream_t stream) {
     return sparse_topk<float>(index, q_ptr, q_term, q_weight, n_queries, k, doc_base, cap, growth, sign_mode,
-                              out_scores, out_ids, out_status, ws, ws_bytes, (cudaStream_t)stream);
+                              out_scores, out_ids, out_status, ws, ws_bytes, sync, (cudaStream_t)stream);
 }
 
 int fz_sparse_scores_f64(const fz_postings_t* index, const int32_t* q_ptr, const int32_t* q_term, int n_queries,

@@ -73,9 +73,29 @@ int cand_init(const CandState<ST>& st, int n_queries, cudaStream_t stream);
 // with (-inf, -1) and the number written to out_n (may be NULL).
 template <typename ST>
 int cand_select(const CandState<ST>& st, int n_queries, int k, ST margin, bool final_out, int64_t doc_base,
-                ST* out_scores, int32_t* out_ids, int32_t* out_n, cudaStream_t stream);
+                ST* out_scores, int32_t* out_ids, int32_t* out_n, cudaStream_t stream, const ST* floor = nullptr);
 
 // (rank-th best score of every query's buffer) - margin -> out [n_queries]; the buffers are not modified
-int cand_kth_score(const CandState<float>& st, int n_queries, int rank, float margin, float* out, cudaStream_t stream);
+template <typename ST>
+int cand_kth_score(const CandState<ST>& st, int n_queries, int rank, ST margin, ST* out, cudaStream_t stream);
+
+// Cross-shard threshold exchange of a sharded corpus (fz_shard_sync_t): between rounds every shard publishes the
+// ceil(k / n_shards)-th best score it holds, the caller's hook all-reduces (MIN) the buffer, and the result becomes a
+// floor under every shard's threshold.  Returns the floor to hand to cand_select, or nullptr when there is no hook.
+template <typename ST>
+inline const ST* shard_floor(const fz_shard_sync_t* sync, const CandState<ST>& st, int n_queries, int k, ST margin,
+                             cudaStream_t stream, int* rc) {
+    *rc = FZ_OK;
+    if (!sync || !sync->hook) return nullptr;
+    const int rank = (k + sync->n_shards - 1) / sync->n_shards;
+    *rc = cand_kth_score<ST>(st, n_queries, rank, margin, (ST*)sync->exchange, stream);
+    if (*rc) return nullptr;
+    if (sync->hook(sync->user) != 0) {
+        set_error("shard sync hook failed");
+        *rc = FZ_ERR_ARG;
+        return nullptr;
+    }
+    return (const ST*)sync->exchange;
+}
 
 }  // namespace fz

@@ -56,11 +56,21 @@ class HybridSearcher:
     def __init__(self, lexical: LexicalIndex | None = None, sparse: SparseIndex | None = None,
                  dense: DenseIndex | None = None, tokens: TokenStore | None = None, k: int = 1000,
                  fusion: str = "nsf", normalization: str | None = "z-score", weights: dict | None = None,
-                 colbert_pool: int | None = None, dense_exact: bool = True, group=None):
+                 colbert_pool: int | None = None, dense_exact: bool = True, group=None, shard_sync: bool = True):
         self.lexical, self.sparse, self.dense, self.tokens = lexical, sparse, dense, tokens
         self.k, self.fusion, self.normalization, self.weights = k, fusion, normalization, weights
         self.colbert_pool, self.dense_exact, self.group = colbert_pool, dense_exact, group
         self.world, self.rank = sharding._world(group)
+        # cross-shard threshold exchange (ops.ShardSync): every shard follows the round schedule of the largest shard
+        self.shard_sync = shard_sync and self.world > 1
+        self._sync = {}
+        if self.shard_sync:
+            idx = {"bm25": lexical, "splade": sparse, "dpr": dense}
+            names = [n for n, ix in idx.items() if ix is not None]
+            dev = torch.device("cuda", torch.cuda.current_device())
+            sizes = sharding.allreduce_max_ints([idx[n].n_docs for n in names], dev, group)
+            reduce = lambda t: sharding.allreduce_min(t, self.group)       # noqa: E731
+            self._sync = {n: ops.ShardSync(reduce, self.world, m) for n, m in zip(names, sizes)}
         self.stage_ms: dict[str, float] = {}
         self.timing = False
         self._events = []
@@ -103,16 +113,17 @@ class HybridSearcher:
                 reduce = (lambda t: sharding.allreduce_min(t, self.group)) if (exact and self.world > 1) else None
                 return ops.dense_topk(q16, self.dense.d_bf16, q32 if exact else None, self.dense.d_f32 if exact else None,
                                       self.k, margin=self._dense_margin() if exact else 0.0, doc_base=self.dense.doc_base,
-                                      tau_reduce=reduce, n_shards=self.world)
+                                      tau_reduce=reduce, n_shards=self.world,
+                                      sched_docs=self._sync["dpr"].sched_docs if (reduce and "dpr" in self._sync) else None)
             s, i = self._timed("dpr", run_dense)
             out["dpr"] = self._timed("dpr_merge", lambda: self._merge(s, i))
         if self.sparse is not None:
             s, i = self._timed("splade", lambda: ops.sparse_topk(self.sparse.view(), q.sp_ptr, q.sp_term, q.sp_weight,
-                                                                  self.k, self.sparse.doc_base))
+                                                                  self.k, self.sparse.doc_base, sync=self._sync.get("splade")))
             out["splade"] = self._timed("splade_merge", lambda: self._merge(s, i))
         if self.lexical is not None:
             s, i = self._timed("bm25", lambda: ops.sparse_topk(self.lexical.view(), q.lex_ptr, q.lex_term, None, self.k,
-                                                                self.lexical.doc_base))
+                                                                self.lexical.doc_base, sync=self._sync.get("bm25")))
             out["bm25"] = self._timed("bm25_merge", lambda: self._merge(s, i))
         if self.tokens is not None:
             out["colbert"] = self._timed("colbert", lambda: self._colbert(q, out))

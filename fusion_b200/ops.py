@@ -254,30 +254,71 @@ class PostingsView:
 MAX_QUERY_TERMS = 128     # kMaxTerms in csrc/sparse.cu: the terms of a query are held once per CTA
 
 
+@dataclass
+class ShardSync:
+    """Cross-shard threshold exchange of a sharded corpus (``fz_shard_sync_t``): ``reduce_min`` all-reduces a [Q] tensor
+    over the shards in place (element-wise MIN, on the current stream); ``sched_docs`` is the largest shard's size, so
+    that every shard runs the same number of rounds and therefore the same number of collectives."""
+    reduce_min: object
+    n_shards: int
+    sched_docs: int
+
+
+class _SyncCall:
+    """Owns the exchange tensor and the ctypes callback of one library call."""
+
+    def __init__(self, sync: "ShardSync | None", nq: int, dtype, device):
+        self.error = None
+        self.struct = None
+        if sync is None or sync.n_shards <= 1:
+            return
+        self.exchange = torch.empty((nq,), dtype=dtype, device=device)
+
+        def hook(_user):
+            try:
+                sync.reduce_min(self.exchange)
+                return 0
+            except BaseException as e:      # an exception must not unwind through the C frames
+                self.error = e
+                return 1
+
+        self._cb = _lib.SHARD_HOOK(hook)
+        self.struct = _lib.ShardSync(self._cb, None, self.exchange.data_ptr(), int(sync.n_shards), int(sync.sched_docs))
+
+    def ref(self):
+        return C.byref(self.struct) if self.struct is not None else None
+
+    def reraise(self):
+        if self.error is not None:
+            raise self.error
+
+
 def _check_query_lengths(q_ptr: torch.Tensor) -> None:
     if q_ptr.numel() > 1 and int((q_ptr[1:] - q_ptr[:-1]).max()) > MAX_QUERY_TERMS:
         raise FusionB200Error(f"a query has more than {MAX_QUERY_TERMS} terms (tokens, duplicates counted); "
                               "the inverted-index kernels hold a query's terms in shared memory")
 
 
-def _sparse_topk_once(pv: PostingsView, q_ptr, q_term, q_weight, k, doc_base, cap, growth, sign_mode):
+def _sparse_topk_once(pv: PostingsView, q_ptr, q_term, q_weight, k, doc_base, cap, growth, sign_mode, sync=None):
     lib = _lib.load()
     f64 = pv.dtype == torch.float64
     dev = pv.term_ptr.device
     nq = q_ptr.numel() - 1
+    sc = _SyncCall(sync, nq, pv.dtype, dev)
     out_s = torch.empty((nq, k), dtype=pv.dtype, device=dev)
     out_i = torch.empty((nq, k), dtype=torch.int32, device=dev)
     status = torch.empty((nq,), dtype=torch.int32, device=dev)
     ws = _ws(lib.fz_sparse_topk_workspace_bytes(nq, k, cap, 1 if f64 else 0), dev)
     st = pv.c_struct()
     if f64:
-        check(lib.fz_sparse_topk_f64(C.byref(st), _ptr(q_ptr), _ptr(q_term), nq, k, doc_base, cap, growth, sign_mode,
-                                     _ptr(out_s), _ptr(out_i), _ptr(status), _ptr(ws), ws.numel(), _stream(out_s)),
-              "fz_sparse_topk_f64")
+        rc = lib.fz_sparse_topk_f64(C.byref(st), _ptr(q_ptr), _ptr(q_term), nq, k, doc_base, cap, growth, sign_mode,
+                                    _ptr(out_s), _ptr(out_i), _ptr(status), _ptr(ws), ws.numel(), sc.ref(), _stream(out_s))
     else:
-        check(lib.fz_sparse_topk_f32(C.byref(st), _ptr(q_ptr), _ptr(q_term), _ptr(q_weight), nq, k, doc_base, cap,
-                                     growth, sign_mode, _ptr(out_s), _ptr(out_i), _ptr(status), _ptr(ws), ws.numel(),
-                                     _stream(out_s)), "fz_sparse_topk_f32")
+        rc = lib.fz_sparse_topk_f32(C.byref(st), _ptr(q_ptr), _ptr(q_term), _ptr(q_weight), nq, k, doc_base, cap,
+                                    growth, sign_mode, _ptr(out_s), _ptr(out_i), _ptr(status), _ptr(ws), ws.numel(),
+                                    sc.ref(), _stream(out_s))
+    sc.reraise()
+    check(rc, "fz_sparse_topk_f64" if f64 else "fz_sparse_topk_f32")
     return out_s, out_i, status
 
 
@@ -295,12 +336,17 @@ def _subset_queries(q_ptr, q_term, q_weight, sel):
 
 
 def sparse_topk(pv: PostingsView, q_ptr, q_term, q_weight, k: int, doc_base: int = 0, cap: int = DEFAULT_CAP,
-                growth: int = DEFAULT_GROWTH):
+                growth: int = DEFAULT_GROWTH, sync: ShardSync | None = None):
     """Top-k of sum_t w_qt * val[t, d] over an inverted index -> (scores [Q,k], ids [Q,k] int32).
 
     Order: score desc, ties by lower doc id; docs that match nothing score 0 and fill up in doc-id order; negative
     scores (BM25 idf < 0 for df > N/2) rank after the zeros - exactly the reference's `sorted(..., reverse=True)`
-    over every document (src/retrievers/bm25.py:100-106)."""
+    over every document (src/retrievers/bm25.py:100-106).
+
+    ``sync`` (corpus sharded over several GPUs): the shards agree on a per-query score floor between rounds, so each
+    keeps only what can still reach the GLOBAL top-k; the local list may then hold fewer than k real entries (padded
+    with (-inf, -1)), the merge of the shards' lists is unchanged.  The rare re-runs below never use it: they are
+    decided per rank and must not issue collectives."""
     q_ptr = _req(q_ptr, torch.int32, "q_ptr")
     q_term = _req(q_term, torch.int32, "q_term")
     if q_weight is not None:
@@ -308,7 +354,7 @@ def sparse_topk(pv: PostingsView, q_ptr, q_term, q_weight, k: int, doc_base: int
     _check_query_lengths(q_ptr)
     k_eff = min(k, pv.n_docs)
     cap = max(cap, 2 * k_eff)
-    out_s, out_i, status = _sparse_topk_once(pv, q_ptr, q_term, q_weight, k_eff, doc_base, cap, growth, +1)
+    out_s, out_i, status = _sparse_topk_once(pv, q_ptr, q_term, q_weight, k_eff, doc_base, cap, growth, +1, sync)
     st = status.cpu()
     over = (st & FZ_STATUS_OVERFLOW) != 0
     if bool(over.any()):            # rare: redo those queries with rounds that cannot overflow
@@ -379,14 +425,16 @@ def normalize_rows(x: torch.Tensor, normalize: bool = True, want_f32: bool = Tru
 
 
 def dense_topk(q_bf16, d_bf16, q_f32, d_f32, k: int, margin: float = 0.0, doc_base: int = 0,
-               cap: int = DEFAULT_CAP, growth: int = DEFAULT_GROWTH, tau_reduce=None, n_shards: int = 1):
+               cap: int = DEFAULT_CAP, growth: int = DEFAULT_GROWTH, tau_reduce=None, n_shards: int = 1,
+               sched_docs: int | None = None):
     """Exhaustive inner-product top-k (tcgen05 GEMM with the threshold filter in its epilogue).
 
     q_bf16 [Q, d], d_bf16 [N, d] are the tensor-core operands; with q_f32 / d_f32 the survivors within ``margin`` of
     the running k-th bf16 score are rescored in fp32 (exact mode).  -> (scores f32 [Q,k], ids int32 [Q,k]).
     ``tau_reduce`` (exact mode, corpus sharded over ``n_shards``): a callable that takes the element-wise MINIMUM of a [Q]
     tensor over the shards (one all-reduce).  Every shard reports its ceil(k / n_shards)-th best score; the minimum
-    bounds the global k-th score from below, and candidates under it (minus the margin) are not rescored."""
+    bounds the global k-th score from below, and candidates under it (minus the margin) are not rescored.  With
+    ``sched_docs`` (largest shard size) the same exchange also runs between the filter rounds (``ShardSync``)."""
     lib = _lib.load()
     q_bf16 = _req(q_bf16, torch.bfloat16, "q_bf16")
     d_bf16 = _req(d_bf16, torch.bfloat16, "d_bf16")
@@ -405,12 +453,16 @@ def dense_topk(q_bf16, d_bf16, q_f32, d_f32, k: int, margin: float = 0.0, doc_ba
     staged = exact and tau_reduce is not None
     tau = torch.empty((nq,), dtype=torch.float32, device=q_bf16.device) if staged else None
 
-    def run(g):
+    def run(g, first=False):
         if staged:
-            check(lib.fz_dense_topk_filter(_ptr(q_bf16), _ptr(d_bf16), nq, n, dim, k_eff, float(margin), doc_base, cap, g,
-                                           min(k_eff, -(-k // max(1, n_shards))), _ptr(tau), _ptr(status), _ptr(ws),
-                                           ws.numel(), _stream(out_s)),
-                  "fz_dense_topk_filter")
+            # only the first attempt exchanges thresholds: a re-run is decided per rank and must not issue collectives
+            sc = _SyncCall(ShardSync(tau_reduce, n_shards, sched_docs) if (first and sched_docs is not None) else None,
+                           nq, torch.float32, q_bf16.device)
+            rc = lib.fz_dense_topk_filter(_ptr(q_bf16), _ptr(d_bf16), nq, n, dim, k_eff, float(margin), doc_base, cap, g,
+                                          min(k_eff, -(-k // max(1, n_shards))), _ptr(tau), _ptr(status), _ptr(ws),
+                                          ws.numel(), sc.ref(), _stream(out_s))
+            sc.reraise()
+            check(rc, "fz_dense_topk_filter")
         else:
             check(lib.fz_dense_topk(_ptr(q_bf16), _ptr(d_bf16), _ptr(q_f32 if exact else None),
                                     _ptr(d_f32 if exact else None), nq, n, dim, k_eff, float(margin), doc_base, cap, g,
@@ -421,7 +473,7 @@ def dense_topk(q_bf16, d_bf16, q_f32, d_f32, k: int, margin: float = 0.0, doc_ba
     # survivors of the plain filter, so the doc ranges may only grow 3x per round instead of 4x.
     if margin > 0:
         growth = min(growth, 3)
-    run(growth)
+    run(growth, first=True)
     if bool(((status & FZ_STATUS_OVERFLOW) != 0).any()):
         if margin > 0:
             run(2)

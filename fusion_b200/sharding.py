@@ -49,11 +49,23 @@ def allreduce_lexical_stats(n_local: int, df_local: np.ndarray, sum_dl_local: in
 
 
 def allreduce_min(t: torch.Tensor, group=None) -> torch.Tensor:
-    """Element-wise minimum over the ranks (in place): the cross-shard rescoring floor of the exact dense mode."""
+    """Element-wise minimum over the ranks (in place): the cross-shard score floors (``ops.ShardSync``, and the rescoring
+    floor of the exact dense mode)."""
     world, _ = _world(group)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
     return t
+
+
+def allreduce_max_ints(values: list[int], device, group=None) -> list[int]:
+    """Element-wise maximum of a few host integers over the ranks (the largest shard size per index: every shard
+    follows the round schedule of the largest one, so all ranks issue the same collectives)."""
+    world, _ = _world(group)
+    if world == 1:
+        return [int(v) for v in values]
+    t = torch.tensor(values, dtype=torch.int64).to(device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return [int(v) for v in t.cpu().tolist()]
 
 
 def gather_topk(scores: torch.Tensor, ids: torch.Tensor, group=None):

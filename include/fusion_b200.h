@@ -141,6 +141,27 @@ int fz_hash_tokens(const void* utf8, int64_t n_bytes, const int64_t* starts, int
 int fz_quantiles_f64(const double* sorted, int64_t n, int n_quantiles, double* out, fz_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Cross-shard threshold exchange of a corpus sharded over G GPUs (north-star "multi-GPU partitioning": each GPU keeps a
+ * local top-k; the reference has no counterpart - its corpus lives in one process).  Without it every shard maintains its
+ * own top-k and emits / selects ~k candidates per query and round whatever G is - a per-query cost that does not shrink
+ * with the shard.  With it, between two rounds of a threshold-filter top-k every shard writes the ceil(k / n_shards)-th
+ * best score it holds into `exchange`, calls `hook` - the caller all-reduces (MIN) the buffer in place on the call's
+ * stream (NCCL through torch.distributed in fusion_b200/sharding.py) - and uses the result as a floor: at least k
+ * documents over all shards reach it, so nothing below it can enter the global top-k (ties with it are kept: the
+ * global tie-break is by document id).  Every shard then carries ~k / G candidates per query.
+ *   sched_docs: the largest shard's n_docs; the round schedule is derived from it so that all shards call the hook the
+ *   same number of times (a shard that runs out of documents runs empty rounds).
+ * Results are unchanged: the union of the shards' lists still contains the global top-k. */
+typedef int (*fz_shard_hook_t)(void* user);
+typedef struct fz_shard_sync {
+    fz_shard_hook_t hook;   /* NULL = no exchange */
+    void* user;
+    void* exchange;         /* device [n_queries] of the score type (double for _f64, float otherwise) */
+    int32_t n_shards;
+    int64_t sched_docs;
+} fz_shard_sync_t;
+
+/* ------------------------------------------------------------------------------------------------------------
  * SPLADE activation head: between the encoder's MLM logits and the CSR vectors K2 consumes.
  * fz_splade_pool: activations[b, v] = sum_l or amax_l log1p(relu(logits[b, l, v] * mask[b, l]))
  *   (SPLADE.forward, src/retrievers/splade/splade.py:88-94).  logits [n_rows, seq_len, vocab] fp32 or bf16, row-major;
@@ -218,10 +239,12 @@ int fz_lexical_impacts(const int64_t* term_ptr, const int32_t* post_doc, const i
 size_t fz_sparse_topk_workspace_bytes(int n_queries, int k, int cap, int is_f64);
 int fz_sparse_topk_f64(const fz_postings_t* index, const int32_t* q_ptr, const int32_t* q_term, int n_queries, int k,
                        int64_t doc_base, int cap, int growth, int sign_mode, double* out_scores, int32_t* out_ids,
-                       int32_t* out_status, void* ws, size_t ws_bytes, fz_stream_t stream);
+                       int32_t* out_status, void* ws, size_t ws_bytes, const fz_shard_sync_t* sync /* may be NULL */,
+                       fz_stream_t stream);
 int fz_sparse_topk_f32(const fz_postings_t* index, const int32_t* q_ptr, const int32_t* q_term, const float* q_weight,
                        int n_queries, int k, int64_t doc_base, int cap, int growth, int sign_mode, float* out_scores,
-                       int32_t* out_ids, int32_t* out_status, void* ws, size_t ws_bytes, fz_stream_t stream);
+                       int32_t* out_ids, int32_t* out_status, void* ws, size_t ws_bytes,
+                       const fz_shard_sync_t* sync /* may be NULL */, fz_stream_t stream);
 /* every document's score: out [n_queries, n_docs] (full-ranking mode and tests) */
 int fz_sparse_scores_f64(const fz_postings_t* index, const int32_t* q_ptr, const int32_t* q_term, int n_queries,
                          double* out_scores, fz_stream_t stream);
@@ -251,7 +274,7 @@ int fz_dense_topk(const void* q_bf16, const void* d_bf16, const float* q_f32, co
  * fz_dense_topk == _filter + _finish(tau_floor = NULL). */
 int fz_dense_topk_filter(const void* q_bf16, const void* d_bf16, int n_queries, int64_t n_docs, int dim, int k, float margin,
                          int64_t doc_base, int cap, int growth, int floor_rank, float* out_tau, int32_t* out_status,
-                         void* ws, size_t ws_bytes, fz_stream_t stream);
+                         void* ws, size_t ws_bytes, const fz_shard_sync_t* sync /* may be NULL */, fz_stream_t stream);
 int fz_dense_topk_finish(const float* q_f32, const float* d_f32, const float* tau_floor, int n_queries, int dim, int k,
                          int64_t doc_base, int cap, float* out_scores, int32_t* out_ids, int32_t* out_status, void* ws,
                          size_t ws_bytes, fz_stream_t stream);

@@ -64,7 +64,7 @@ def main():
 
     # single-index answer, computed locally without collectives
     saved = dist.group.WORLD
-    full = HybridSearcher(*build(0, n_docs), k=k, fusion="nsf", normalization="z-score")
+    full = HybridSearcher(*build(0, n_docs), k=k, fusion="nsf", normalization="z-score", shard_sync=False)
     full.world, full.rank = 1, 0
     lists_f = full.retrieve(q)
     fused_f = full.fuse(lists_f)

@@ -83,6 +83,33 @@ def test_dense_topk_bf16_mode_overlap():
     assert hit / tot >= 0.999
 
 
+def test_dense_exact_shards_with_cross_shard_floor():
+    """Staged exact mode with the threshold exchange between the filter rounds (emulated all-reduce, uneven shards: the
+    small shard runs empty rounds so that every shard issues the same collectives): merged == unsharded."""
+    from fusion_b200 import ops
+    nq, n, d, k, margin, cap = 24, 30000, 128, 100, 0.008, 512
+    q = torch.from_numpy(synth.dense_embeddings(nq, d, seed=11)).cuda()
+    docs = torch.from_numpy(synth.dense_embeddings(n, d, seed=12)).cuda()
+    q32, q16 = ops.normalize_rows(q)
+    d32, d16 = ops.normalize_rows(docs)
+    sc, ids = ops.dense_topk(q16, d16, q32, d32, k, margin=margin, cap=cap)
+    floor = sc[:, -1] - margin                       # every true top-k doc has a bf16 score above this
+    counts, parts = [], []
+    bounds = ((0, 13000), (13000, 24000), (24000, n))
+    for lo, hi in bounds:
+        calls = []
+
+        def fake_min(t):
+            calls.append(1)
+            return torch.minimum(t, floor, out=t)
+        parts.append(ops.dense_topk(q16, d16[lo:hi].contiguous(), q32, d32[lo:hi].contiguous(), k, margin=margin, doc_base=lo,
+                                    cap=cap, tau_reduce=fake_min, n_shards=3, sched_docs=13000))
+        counts.append(len(calls))
+    assert len(set(counts)) == 1 and counts[0] >= 3
+    ms, mi = ops.merge_topk(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]), k)
+    assert torch.equal(mi, ids) and torch.equal(ms, sc)
+
+
 @pytest.mark.parametrize("lq,n_cand,max_len", [(64, 40, 300), (32, 33, 300), (128, 7, 300), (64, 70, 900), (17, 100, 60)])
 def test_maxsim_vs_oracle(lq, n_cand, max_len):
     """Doc lengths 1..max_len (passages longer than one MMA group are cut into 2-4 pieces), candidates outside the

@@ -107,6 +107,78 @@ def test_bm25_sharded_equals_unsharded():
     assert torch.equal(mi, ids) and torch.equal(ms, sc)
 
 
+@pytest.mark.parametrize("mode", ["min_with_true_kth", "true_kth"])
+@pytest.mark.parametrize("duplicate_halves", [False, True])
+def test_bm25_shards_with_cross_shard_floor(mode, duplicate_halves):
+    """ops.ShardSync on one GPU: the shards run one after the other and the all-reduce is emulated by a hook that folds in
+    the TRUE global k-th score (a valid floor: k documents reach it).  The merged lists must equal the unsharded run bit
+    for bit - including exact score ties across shards (second half of the corpus = copy of the first), where the doc
+    that ties the floor on a low-id shard must survive."""
+    from fusion_b200 import ops
+    from fusion_b200.index import LexicalIndex
+    n_docs, vocab, k, cap = 24000, 3000, 200, 1024
+    (dptr, dtok), (qptr, qtok) = synth.c3_lexical(n_docs, 24, vocab)
+    if duplicate_halves:
+        half = n_docs // 2
+        toks = dtok[:dptr[half]]
+        dtok = np.concatenate([toks, toks])
+        lens = np.diff(dptr[:half + 1])
+        dptr = np.concatenate([[0], np.cumsum(np.concatenate([lens, lens]))]).astype(np.int64)
+    full = LexicalIndex(dptr, dtok, vocab, "bm25", 0.9, 0.4, tile_docs=1024)
+    q_ptr, q_term = _token_queries(qptr, qtok, vocab, full.device)
+    sc, ids = ops.sparse_topk(full.view(), q_ptr, q_term, None, k, cap=cap)
+    kth = sc[:, -1].clone()
+    bounds = [(0, 8000), (8000, 16000), (16000, n_docs)]
+    calls = []
+
+    def fake_allreduce_min(t):
+        calls.append(1)
+        if mode == "true_kth":
+            t.copy_(kth)
+        else:
+            torch.minimum(t, kth, out=t)
+        return t
+
+    parts = []
+    for lo, hi in bounds:
+        p = dptr[lo:hi + 1] - dptr[lo]
+        t = dtok[dptr[lo]:dptr[hi]]
+        ix = LexicalIndex(p, t, vocab, "bm25", 0.9, 0.4, doc_base=lo, tile_docs=1024, global_n_docs=n_docs,
+                          global_df=full.df, global_sum_dl=int(dptr[-1]))
+        parts.append(ops.sparse_topk(ix.view(), q_ptr, q_term, None, k, doc_base=lo, cap=cap,
+                                     sync=ops.ShardSync(fake_allreduce_min, len(bounds), 8000)))
+        calls.append(0)
+    per_shard = [len(x) for x in "".join(map(str, calls)).split("0") if x]
+    assert len(per_shard) == 3 and len(set(per_shard)) == 1 and per_shard[0] >= 2    # same number of exchanges everywhere
+    ms, mi = ops.merge_topk(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]), k)
+    assert torch.equal(mi, ids) and torch.equal(ms, sc)
+    # the floor prunes: a shard keeps far fewer than k real entries for most queries
+    kept = torch.stack([(p[1] >= 0).sum(1) for p in parts]).float().mean()
+    assert kept < 0.8 * k
+
+
+def test_splade_shards_with_cross_shard_floor():
+    from fusion_b200 import ops
+    from fusion_b200.index import SparseIndex, sparse_queries
+    vocab, n_docs, nq, k, cap = 2000, 18000, 16, 100, 512
+    dp, dt, dw = synth.splade_vectors(n_docs, vocab, 60, 8, 200, seed=311)
+    qp, qt, qw = synth.splade_vectors(nq, vocab, 12, 2, 40, seed=312)
+    full = SparseIndex(dp, dt, dw, vocab, "cos_sim", tile_docs=1024, tiled_min=64)
+    q_ptr, q_term, q_w = sparse_queries(qp, qt, qw, "cos_sim", full.device)
+    sc, ids = ops.sparse_topk(full.view(), q_ptr, q_term, q_w, k, cap=cap)
+    kth = sc[:, -1].clone()
+    parts = []
+    for lo, hi in ((0, 6000), (6000, 12000), (12000, n_docs)):
+        ix = SparseIndex(dp[lo:hi + 1] - dp[lo], dt[dp[lo]:dp[hi]], dw[dp[lo]:dp[hi]], vocab, "cos_sim", doc_base=lo,
+                         tile_docs=1024, tiled_min=64)
+        parts.append(ops.sparse_topk(ix.view(), q_ptr, q_term, q_w, k, doc_base=lo, cap=cap,
+                                     sync=ops.ShardSync(lambda t: torch.minimum(t, kth, out=t), 3, 6000)))
+    ms, mi = ops.merge_topk(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]), k)
+    # shard-local accumulation order differs from the full index's (different storage forms per shard): fp32 tolerance
+    torch.testing.assert_close(ms, sc, rtol=1e-5, atol=1e-6)
+    assert float((mi == ids).float().mean()) > 0.98
+
+
 @pytest.mark.parametrize("sim", ["cos_sim", "dot"])
 def test_splade_sparse_vs_dense_oracle(sim):
     """SPLADE: the reference scores dense [.,V] vectors with cosine (hybrid.py:101-103); the inverted index must
