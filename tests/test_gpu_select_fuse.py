@@ -216,3 +216,46 @@ def test_fuse_truncated_output_equals_head_of_full_fusion(method, norm):
         ti, ts, tn = ops.fuse(lists, method, norm, w, out_stride=stride)
         assert torch.equal(ti, full_i[:, :stride]) and torch.equal(ts, full_s[:, :stride])
         assert torch.equal(tn, torch.clamp(full_n, max=stride))
+
+
+def test_ranking_tsv_round_trip_and_msmarco_evaluation(tmp_path):
+    """colbert_ir.py:261-345: ranking file format + recall@depth / MRR@10 / R-precision, against a plain-Python restatement
+    of that loop."""
+    from fusion_b200.utils import colbert_ir as ci
+    rng = np.random.Generator(np.random.PCG64(3))
+    nq, k, pool = 37, 60, 400
+    ids = np.stack([rng.permutation(pool)[:k] for _ in range(nq)]).astype(np.int32)
+    ids[5, 40:] = -1
+    scores = -np.sort(-rng.random((nq, k)), axis=1)
+    golds = [rng.choice(pool, size=int(rng.integers(1, 6)), replace=False).tolist() for _ in range(nq)]
+    qids = list(range(100, 100 + nq))
+    path = str(tmp_path / "ranking.tsv")
+    n = ci.save_ranking_tsv(path, qids, torch.from_numpy(ids), torch.from_numpy(scores))
+    assert n == nq * k - 20
+    q2, i2, s2 = ci.load_ranking_tsv(path)
+    assert q2 == qids and torch.equal(i2, torch.from_numpy(ids))
+    assert torch.equal(s2[ids >= 0], torch.from_numpy(scores)[ids >= 0])
+    # restatement of the reference loop
+    depths = (5, 10, 50)
+    mrr, rp, rec = 0.0, 0.0, {d: 0.0 for d in depths}
+    for qi in range(nq):
+        ranking = [p for p in ids[qi].tolist() if p >= 0]
+        pos = golds[qi]
+        for rank, pid in enumerate(ranking, start=1):
+            if rank <= 10 and pid in pos:
+                mrr += 1.0 / rank
+                break
+        for rank, pid in enumerate(ranking, start=1):
+            if rank <= len(pos) and pid in pos:
+                rp += 1.0 / len(pos)
+            if pid in pos:
+                for d in depths:
+                    if rank <= d:
+                        rec[d] += 1.0 / len(pos)
+    gp = torch.tensor(np.concatenate([[0], np.cumsum([len(g) for g in golds])]), dtype=torch.int32).cuda()
+    gi = torch.tensor([x for g in golds for x in g], dtype=torch.int32).cuda()
+    got = ci.evaluate_ranking_tensors(i2.cuda(), gp, gi, depths=depths)
+    assert got["mrr@10"] == pytest.approx(mrr / nq, abs=1e-12)
+    assert got["rp"] == pytest.approx(rp / nq, abs=1e-12)
+    for d in depths:
+        assert got[f"recall@{d}"] == pytest.approx(rec[d] / nq, abs=1e-12)
