@@ -434,7 +434,8 @@ def main():
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     tf_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
-    peak_src = "measured (MEASURED_PEAKS.json, sustained bf16)" if peaks else "fallback (B200_PROFILING.md)"
+    peak_src = ("measured (MEASURED_PEAKS.json: HBM copy GB/s for hbm-bound kernels, sustained bf16 TFLOP/s for tensor-bound ones)"
+                if peaks else "fallback (B200_PROFILING.md)")
 
     # DRAM bytes of ONE captured launch (the largest round) from the committed `ncu --set full` pass, profiles/traffic.json;
     # it belongs to the profiled configuration (1 GPU, full size) and is reported as captured, not rescaled.
