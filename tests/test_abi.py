@@ -42,3 +42,31 @@ def test_postings_struct_matches_header_layout():
     # fz_postings_t: 10 pointers, int64 dense_stride, 6 x int32, int64 n_docs
     assert ctypes.sizeof(_lib.Postings) == 10 * 8 + 8 + 6 * 4 + 8
     assert _lib.Postings.n_docs.offset == 10 * 8 + 8 + 6 * 4 and _lib.Postings.dense_stride.offset == 80
+
+
+def test_shard_sync_struct_matches_header_layout():
+    from fusion_b200 import _lib
+    # fz_shard_sync_t: hook, user, exchange pointers, int32 n_shards (+ 4 bytes padding), int64 sched_docs
+    assert ctypes.sizeof(_lib.ShardSync) == 3 * 8 + 8 + 8
+    assert _lib.ShardSync.n_shards.offset == 24 and _lib.ShardSync.sched_docs.offset == 32
+
+
+def test_header_is_plain_c_and_layouts_match_ctypes(tmp_path):
+    """include/fusion_b200.h must be consumable from C (cgo / JNI / ctypes-style bindings): compile it with gcc -std=c99
+    and compare the struct layouts the compiler sees with the ctypes mirrors."""
+    import shutil
+    import subprocess
+    from fusion_b200 import _lib
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "hdr_check.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "fusion_b200.h"\n'
+                   'int main(void) { printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(fz_shard_sync_t), offsetof(fz_shard_sync_t, n_shards),\n'
+                   '  offsetof(fz_shard_sync_t, sched_docs), sizeof(fz_postings_t), offsetof(fz_postings_t, n_docs),\n'
+                   '  offsetof(fz_postings_t, dense_stride)); return 0; }\n')
+    exe = tmp_path / "hdr_check"
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert got == [ctypes.sizeof(_lib.ShardSync), _lib.ShardSync.n_shards.offset, _lib.ShardSync.sched_docs.offset,
+                   ctypes.sizeof(_lib.Postings), _lib.Postings.n_docs.offset, _lib.Postings.dense_stride.offset]

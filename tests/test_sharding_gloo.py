@@ -24,6 +24,53 @@ def _np_merge(gs, gi, k):
     return out_s, out_i
 
 
+def _floor_protocol(rank, world, scores, k):
+    """Host restatement of the threshold exchange of ``fz_shard_sync_t`` (rounds over the shard, local ceil(k/G)-th best,
+    all-reduce MIN, keep everything at or above the floor, ties included): the merged shard lists are the global top-k,
+    every rank issues the same number of collectives although the shards differ in size."""
+    nq, n_docs = scores.shape
+    lo, hi = sharding.shard_bounds(n_docs, world, rank)
+    sched = sharding.allreduce_max_ints([hi - lo], "cpu")[0]
+    rank_floor = -(-k // world)
+    cand = [[] for _ in range(nq)]                       # (score, global id)
+    tau = np.full(nq, -np.inf)
+    r_lo, r_hi, n_coll = 0, min(sched, 8), 0
+    while True:
+        for q in range(nq):
+            for d in range(min(r_lo, hi - lo), min(r_hi, hi - lo)):
+                s = scores[q, lo + d]
+                if s > tau[q]:
+                    cand[q].append((s, lo + d))
+        last = r_hi >= sched
+        if not last:
+            loc = torch.tensor([sorted((c[0] for c in cand[q]), reverse=True)[rank_floor - 1] if len(cand[q]) >= rank_floor
+                                else -np.inf for q in range(nq)], dtype=torch.float64)
+            floor = sharding.allreduce_min(loc).numpy()
+            n_coll += 1
+        for q in range(nq):
+            best = sorted(cand[q], key=lambda c: (-c[0], c[1]))
+            if len(best) >= k:
+                best = best[:k]
+                tau[q] = max(tau[q], best[-1][0])        # strict: a later local doc that ties loses (higher id)
+            if not last and np.isfinite(floor[q]):
+                best = [c for c in best if c[0] >= floor[q]]
+                tau[q] = max(tau[q], np.nextafter(floor[q], -np.inf))   # ties with the floor stay
+            cand[q] = best
+        if last:
+            break
+        r_lo, r_hi = r_hi, min(sched, r_hi * 2)
+    counts = sharding.allreduce_max_ints([n_coll, -n_coll], "cpu")
+    assert counts[0] == n_coll and -counts[1] == n_coll           # same number of collectives on every rank
+    ls = torch.full((nq, k), float("-inf"), dtype=torch.float64)
+    li = torch.full((nq, k), -1, dtype=torch.int32)
+    for q in range(nq):
+        for j, (s, d) in enumerate(cand[q][:k]):
+            ls[q, j], li[q, j] = s, d
+    ms, mi = sharding.gather_merge_topk(ls, li, k, merge=_np_merge)
+    ref = np.stack([np.lexsort((np.arange(n_docs), -scores[q]))[:k] for q in range(nq)])
+    assert np.array_equal(mi.numpy(), ref)
+
+
 def _worker(rank, world, port, n_docs, nq, k, ret):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -56,6 +103,13 @@ def _worker(rank, world, port, n_docs, nq, k, ret):
         for r in range(world):
             exp[:, r::world] = torch.arange(nq, dtype=torch.float32)[:, None] + r
         assert torch.equal(full, exp)
+        # the helpers of the cross-shard threshold exchange
+        assert sharding.allreduce_max_ints([hi - lo, 7 + rank], "cpu") == [max(h - l for l, h in
+                                                                               (sharding.shard_bounds(n_docs, world, r) for r in range(world))),
+                                                                           7 + world - 1]
+        t = torch.tensor([float(rank), 5.0 - rank, float("-inf") if rank == 0 else 3.0], dtype=torch.float64)
+        assert sharding.allreduce_min(t).tolist() == [0.0, 5.0 - (world - 1), float("-inf")]
+        _floor_protocol(rank, world, scores, k)
         ret[rank] = True
     finally:
         dist.destroy_process_group()
@@ -66,6 +120,14 @@ def test_two_rank_topk_exchange():
     ret = mgr.dict()
     mp.spawn(_worker, args=(2, 29641, 101, 7, 5, ret), nprocs=2, join=True)
     assert ret.get(0) and ret.get(1)
+
+
+def test_three_rank_uneven_shards():
+    """100 docs over 3 ranks (34 / 33 / 33): the small shards run an empty last round so the collectives line up."""
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(3, 29651, 100, 5, 6, ret), nprocs=3, join=True)
+    assert all(ret.get(r) for r in range(3))
 
 
 def test_shard_bounds_cover_the_corpus():
