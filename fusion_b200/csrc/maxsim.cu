@@ -12,11 +12,12 @@
 // two 64-dim halves as 128-byte rows, rows padded to a multiple of 8, 16-byte chunks pre-swizzled (chunk ^ row % 8).
 // A passage therefore arrives with two plain bulk copies of exactly its bytes - no tensor map per box height (switching
 // between them serialised the TMA unit), no rounding of the row count to the box, and the bytes of a passage are
-// contiguous in HBM.  A persistent CTA owns whole queries: warp 0 streams the passages into a 3-stage ring of 64 KB
-// groups, warp 1 issues 8 MMAs per group into one of two 256-column TMEM accumulators, two teams of epilogue warps
-// reduce alternate passages.  Packing ~3 passages per group amortises the barrier round trips, the >= 95-cycle issue
-// cost of a tcgen05.mma and the shared-memory reads of the query operand.  The kernel is HBM-bound: 2*Lq = 128 FLOP
-// per bf16 element read.
+// contiguous in HBM.  A persistent CTA owns whole queries: warp 0 streams the passages into a 2-stage ring of 64 KB
+// groups, warp 1 issues 8 MMAs per group into one of two 256-column TMEM accumulators, the eight epilogue warps reduce
+// the passages round-robin in 2 * rep teams (rep = replicas of the query rows in the 128-row A tile, see the kernel).
+// Packing ~3 passages per group amortises the barrier round trips, the >= 95-cycle issue cost of a tcgen05.mma and the
+// shared-memory reads of the query operand; the packing itself is decided once per query by the pre-pass.  The kernel
+// is HBM-bound: 2*Lq = 128 FLOP per bf16 element read.
 #include "common.cuh"
 #include "ptx.cuh"
 
