@@ -67,10 +67,11 @@ class HybridSearcher:
         if self.shard_sync:
             idx = {"bm25": lexical, "splade": sparse, "dpr": dense}
             names = [n for n, ix in idx.items() if ix is not None]
-            dev = torch.device("cuda", torch.cuda.current_device())
-            sizes = sharding.allreduce_max_ints([idx[n].n_docs for n in names], dev, group)
-            reduce = lambda t: sharding.allreduce_min(t, self.group)       # noqa: E731
-            self._sync = {n: ops.ShardSync(reduce, self.world, m) for n, m in zip(names, sizes)}
+            if names:           # (a fusion-only searcher holds no index: nothing to exchange)
+                dev = torch.device("cuda", torch.cuda.current_device())
+                sizes = sharding.allreduce_max_ints([idx[n].n_docs for n in names], dev, group)
+                reduce = lambda t: sharding.allreduce_min(t, self.group)       # noqa: E731
+                self._sync = {n: ops.ShardSync(reduce, self.world, m) for n, m in zip(names, sizes)}
         self.stage_ms: dict[str, float] = {}
         self.timing = False
         self._events = []
