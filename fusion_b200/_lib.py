@@ -36,7 +36,7 @@ SHARD_HOOK = C.CFUNCTYPE(C.c_int, C.c_void_p)      # fz_shard_hook_t
 class ShardSync(C.Structure):
     """mirror of fz_shard_sync_t"""
     _fields_ = [("hook", SHARD_HOOK), ("user", C.c_void_p), ("exchange", C.c_void_p), ("n_shards", C.c_int32),
-                ("sched_docs", C.c_int64)]
+                ("floor_rank", C.c_int32), ("sched_docs", C.c_int64)]
 
 
 _p, _i, _i64, _sz, _f, _d = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_float, C.c_double

@@ -87,7 +87,7 @@ inline const ST* shard_floor(const fz_shard_sync_t* sync, const CandState<ST>& s
                              cudaStream_t stream, int* rc) {
     *rc = FZ_OK;
     if (!sync || !sync->hook) return nullptr;
-    const int rank = (k + sync->n_shards - 1) / sync->n_shards;
+    const int rank = sync->floor_rank > 0 ? sync->floor_rank : (k + sync->n_shards - 1) / sync->n_shards;
     *rc = cand_kth_score<ST>(st, n_queries, rank, margin, (ST*)sync->exchange, stream);
     if (*rc) return nullptr;
     if (sync->hook(sync->user) != 0) {

@@ -267,7 +267,7 @@ class ShardSync:
 class _SyncCall:
     """Owns the exchange tensor and the ctypes callback of one library call."""
 
-    def __init__(self, sync: "ShardSync | None", nq: int, dtype, device):
+    def __init__(self, sync: "ShardSync | None", nq: int, dtype, device, k_global: int = 0):
         self.error = None
         self.struct = None
         if sync is None or sync.n_shards <= 1:
@@ -283,7 +283,11 @@ class _SyncCall:
                 return 1
 
         self._cb = _lib.SHARD_HOOK(hook)
-        self.struct = _lib.ShardSync(self._cb, None, self.exchange.data_ptr(), int(sync.n_shards), int(sync.sched_docs))
+        # the published rank refers to the GLOBAL k: a shard smaller than k runs with k_eff < k and must not count as
+        # ceil(k_eff / G) documents towards the k the floor has to cover
+        floor_rank = -(-int(k_global) // int(sync.n_shards)) if k_global else 0
+        self.struct = _lib.ShardSync(self._cb, None, self.exchange.data_ptr(), int(sync.n_shards), floor_rank,
+                                     int(sync.sched_docs))
 
     def ref(self):
         return C.byref(self.struct) if self.struct is not None else None
@@ -299,12 +303,13 @@ def _check_query_lengths(q_ptr: torch.Tensor) -> None:
                               "the inverted-index kernels hold a query's terms in shared memory")
 
 
-def _sparse_topk_once(pv: PostingsView, q_ptr, q_term, q_weight, k, doc_base, cap, growth, sign_mode, sync=None):
+def _sparse_topk_once(pv: PostingsView, q_ptr, q_term, q_weight, k, doc_base, cap, growth, sign_mode, sync=None,
+                      k_global: int = 0):
     lib = _lib.load()
     f64 = pv.dtype == torch.float64
     dev = pv.term_ptr.device
     nq = q_ptr.numel() - 1
-    sc = _SyncCall(sync, nq, pv.dtype, dev)
+    sc = _SyncCall(sync, nq, pv.dtype, dev, k_global)
     out_s = torch.empty((nq, k), dtype=pv.dtype, device=dev)
     out_i = torch.empty((nq, k), dtype=torch.int32, device=dev)
     status = torch.empty((nq,), dtype=torch.int32, device=dev)
@@ -354,7 +359,7 @@ def sparse_topk(pv: PostingsView, q_ptr, q_term, q_weight, k: int, doc_base: int
     _check_query_lengths(q_ptr)
     k_eff = min(k, pv.n_docs)
     cap = max(cap, 2 * k_eff)
-    out_s, out_i, status = _sparse_topk_once(pv, q_ptr, q_term, q_weight, k_eff, doc_base, cap, growth, +1, sync)
+    out_s, out_i, status = _sparse_topk_once(pv, q_ptr, q_term, q_weight, k_eff, doc_base, cap, growth, +1, sync, k)
     st = status.cpu()
     over = (st & FZ_STATUS_OVERFLOW) != 0
     if bool(over.any()):            # rare: redo those queries with rounds that cannot overflow
@@ -457,7 +462,7 @@ def dense_topk(q_bf16, d_bf16, q_f32, d_f32, k: int, margin: float = 0.0, doc_ba
         if staged:
             # only the first attempt exchanges thresholds: a re-run is decided per rank and must not issue collectives
             sc = _SyncCall(ShardSync(tau_reduce, n_shards, sched_docs) if (first and sched_docs is not None) else None,
-                           nq, torch.float32, q_bf16.device)
+                           nq, torch.float32, q_bf16.device, k)
             rc = lib.fz_dense_topk_filter(_ptr(q_bf16), _ptr(d_bf16), nq, n, dim, k_eff, float(margin), doc_base, cap, g,
                                           min(k_eff, -(-k // max(1, n_shards))), _ptr(tau), _ptr(status), _ptr(ws),
                                           ws.numel(), sc.ref(), _stream(out_s))

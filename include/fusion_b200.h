@@ -147,8 +147,9 @@ int fz_quantiles_f64(const double* sorted, int64_t n, int n_quantiles, double* o
  * with the shard.  With it, between two rounds of a threshold-filter top-k every shard writes the ceil(k / n_shards)-th
  * best score it holds into `exchange`, calls `hook` - the caller all-reduces (MIN) the buffer in place on the call's
  * stream (NCCL through torch.distributed in fusion_b200/sharding.py) - and uses the result as a floor: at least k
- * documents over all shards reach it, so nothing below it can enter the global top-k (ties with it are kept: the
- * global tie-break is by document id).  Every shard then carries ~k / G candidates per query.
+ * documents over all shards reach it (a shard that holds fewer than floor_rank candidates publishes -inf: no floor
+ * that round), so nothing below it can enter the global top-k (ties with it are kept: the global tie-break is by
+ * document id).  Every shard then carries ~k / G candidates per query.
  *   sched_docs: the largest shard's n_docs; the round schedule is derived from it so that all shards call the hook the
  *   same number of times (a shard that runs out of documents runs empty rounds).
  * Results are unchanged: the union of the shards' lists still contains the global top-k. */
@@ -158,6 +159,8 @@ typedef struct fz_shard_sync {
     void* user;
     void* exchange;         /* device [n_queries] of the score type (double for _f64, float otherwise) */
     int32_t n_shards;
+    int32_t floor_rank;     /* rank each shard publishes: ceil(K / n_shards) for the K of the GLOBAL top-K (a small shard
+                               may run with k < K); 0 = ceil(k / n_shards) of this call's k */
     int64_t sched_docs;
 } fz_shard_sync_t;
 

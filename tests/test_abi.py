@@ -46,9 +46,10 @@ def test_postings_struct_matches_header_layout():
 
 def test_shard_sync_struct_matches_header_layout():
     from fusion_b200 import _lib
-    # fz_shard_sync_t: hook, user, exchange pointers, int32 n_shards (+ 4 bytes padding), int64 sched_docs
+    # fz_shard_sync_t: hook, user, exchange pointers, int32 n_shards, int32 floor_rank, int64 sched_docs
     assert ctypes.sizeof(_lib.ShardSync) == 3 * 8 + 8 + 8
-    assert _lib.ShardSync.n_shards.offset == 24 and _lib.ShardSync.sched_docs.offset == 32
+    assert _lib.ShardSync.n_shards.offset == 24 and _lib.ShardSync.floor_rank.offset == 28
+    assert _lib.ShardSync.sched_docs.offset == 32
 
 
 def test_header_is_plain_c_and_layouts_match_ctypes(tmp_path):
@@ -62,11 +63,12 @@ def test_header_is_plain_c_and_layouts_match_ctypes(tmp_path):
         pytest.skip("no gcc")
     src = tmp_path / "hdr_check.c"
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "fusion_b200.h"\n'
-                   'int main(void) { printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(fz_shard_sync_t), offsetof(fz_shard_sync_t, n_shards),\n'
-                   '  offsetof(fz_shard_sync_t, sched_docs), sizeof(fz_postings_t), offsetof(fz_postings_t, n_docs),\n'
-                   '  offsetof(fz_postings_t, dense_stride)); return 0; }\n')
+                   'int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(fz_shard_sync_t), offsetof(fz_shard_sync_t, n_shards),\n'
+                   '  offsetof(fz_shard_sync_t, floor_rank), offsetof(fz_shard_sync_t, sched_docs), sizeof(fz_postings_t),\n'
+                   '  offsetof(fz_postings_t, n_docs), offsetof(fz_postings_t, dense_stride)); return 0; }\n')
     exe = tmp_path / "hdr_check"
     subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
-    assert got == [ctypes.sizeof(_lib.ShardSync), _lib.ShardSync.n_shards.offset, _lib.ShardSync.sched_docs.offset,
-                   ctypes.sizeof(_lib.Postings), _lib.Postings.n_docs.offset, _lib.Postings.dense_stride.offset]
+    assert got == [ctypes.sizeof(_lib.ShardSync), _lib.ShardSync.n_shards.offset, _lib.ShardSync.floor_rank.offset,
+                   _lib.ShardSync.sched_docs.offset, ctypes.sizeof(_lib.Postings), _lib.Postings.n_docs.offset,
+                   _lib.Postings.dense_stride.offset]

@@ -57,7 +57,8 @@ def test_sparse_topk_shard_sync_is_inert_for_one_shard():
     assert ops._SyncCall(None, 4, torch.float32, "cpu").ref() is None
     assert ops._SyncCall(ops.ShardSync(lambda t: t, 1, 100), 4, torch.float32, "cpu").ref() is None
     sc = ops._SyncCall(ops.ShardSync(lambda t: t.fill_(1.0), 2, 100), 4, torch.float32, "cpu")
-    assert sc.ref() is not None and sc.struct.n_shards == 2 and sc.struct.sched_docs == 100
+    assert sc.ref() is not None and sc.struct.n_shards == 2 and sc.struct.sched_docs == 100 and sc.struct.floor_rank == 0
+    assert ops._SyncCall(ops.ShardSync(lambda t: t, 8, 100), 4, torch.float32, "cpu", k_global=1000).struct.floor_rank == 125
     assert sc.struct.hook(None) == 0 and sc.exchange.tolist() == [1.0] * 4          # the callback runs the reduction
 
     def boom(t):
