@@ -365,6 +365,179 @@ __global__ void __launch_bounds__(kMaxSparseThreads) sparse_tile_kernel(const Sp
     }
 }
 
+// ------------------------------------------------------------------------------------ EXPERIMENTAL (off by default)
+// fp32 variant with FIXED-POINT scatter accumulators (FZ_SPLADE_FIXED=1; not yet validated on hardware - the default path
+// is sparse_tile_kernel above).  Why: per (query, 2048-doc tile) a SPLADE query has ~12 active scatter terms that move a
+// median of 32 postings each, so the barrier-per-term scheme keeps ~19 % of the CTA's posting slots busy; fp32 atomicAdd
+// on shared memory is a CAS loop, but a shared INTEGER add is one native instruction (ATOMS.ADD).  Here the scatter terms
+// add round(v * w * 2^24) into int32 accumulators, every warp working through its own terms with no barrier between
+// terms (integer adds commute: the result is deterministic), dense rows stay in fp32 registers, and the scan adds the two
+// parts.  |scatter sum| must stay below 2^31 / scale = 128 (cos_sim: <= 1); absolute error <= n_terms * 2^-25.
+struct TermListFx {
+    long long lo[kMaxTerms];
+    int lenkind[kMaxTerms];
+    float w[kMaxTerms];
+    unsigned ballot[kMaxTerms / 32][2];
+    int n, n_dense;
+};
+constexpr float kFxScale = 16777216.0f;         // 2^24
+constexpr float kFxInv = 1.0f / 16777216.0f;
+
+template <int MODE>
+__global__ void __launch_bounds__(kMaxSparseThreads) sparse_tile_fx_kernel(const SparseArgs<float> A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int* fx = reinterpret_cast<int*>(smem_raw);         // [tile_docs + 4] fixed-point scatter sums, slot tile_docs = dump
+    __shared__ TermStatic S;
+    __shared__ TermListFx L[2];
+    const float* __restrict__ short_val = reinterpret_cast<const float*>(A.ix.post_val);
+    const float* __restrict__ tiled_val = reinterpret_cast<const float*>(A.ix.tiled_val);
+    const float* __restrict__ dense_val = reinterpret_cast<const float*>(A.ix.dense_val);
+    const int T = blockDim.x, t = threadIdx.x, lane = t & 31, warp = t >> 5, n_warps = T >> 5;
+    const int tile_docs = A.ix.tile_docs;
+
+    const int group = A.group_lo + blockIdx.x / A.n_queries;
+    const int q = blockIdx.x % A.n_queries;
+    const int t_begin = max(group * kGroupTiles, A.tile_lo), t_end = min((group + 1) * kGroupTiles, A.tile_hi);
+    resolve_terms<float>(A, q, group, S);
+    const float tau = MODE == 0 ? A.st.tau[q] : 0.0f;
+    const float lim = A.sign_mode > 0 ? (tau > 0.0f ? tau : 0.0f) : tau;
+    if (t == 0) fx[tile_docs] = 0;
+    __syncthreads();
+    uint32_t o0 = tile_offset<float>(A, S, t_begin), o1 = tile_offset<float>(A, S, t_begin + 1);
+    for (int tile = t_begin; tile < t_end; ++tile) {
+        const uint32_t o2 = tile + 1 < t_end ? tile_offset<float>(A, S, tile + 2) : 0;
+        const long long d_lo = (long long)tile * tile_docs;
+        const long long d_hi = min(d_lo + tile_docs, (long long)A.ix.n_docs);
+        const int dl = (int)d_lo;
+        TermListFx& Lt = L[tile & 1];
+        // ---- zero this thread's own accumulator slots (only it reads them back), then the tile's term list
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) *reinterpret_cast<int4*>(fx + (c * T + t) * 4) = make_int4(0, 0, 0, 0);
+        const int n_tw = S.n <= 32 ? 1 : (S.n + 31) >> 5;
+        long long lo = 0;
+        int len = 0, kind = kKindNone;
+        unsigned bd = 0, bs = 0;
+        if (t < 32 * n_tw) {
+            kind = S.kind[t];
+            if (kind == kKindTiled) {
+                lo = S.base[t] + o0;
+                len = (int)(o1 - o0);
+            } else if (kind == kKindDense) {
+                lo = S.base[t] + (long long)tile * tile_docs;
+                len = tile_docs;
+            } else if (kind == kKindShort) {
+                lo = S.base[t];
+                len = S.aux[t];
+            }
+            bd = __ballot_sync(0xffffffffu, len > 0 && kind == kKindDense);
+            bs = __ballot_sync(0xffffffffu, len > 0 && kind != kKindDense);
+            if (n_tw > 1 && lane == 0) { Lt.ballot[warp][0] = bd; Lt.ballot[warp][1] = bs; }
+        }
+        if (n_tw > 1) __syncthreads();
+        if (t < 32 * n_tw) {
+            const unsigned below = (1u << lane) - 1;
+            int dense_before = __popc(bd & below), scat_before = __popc(bs & below), n_dense = __popc(bd), n_scat = __popc(bs);
+            if (n_tw > 1) {
+                n_dense = 0;
+                n_scat = 0;
+                for (int w2 = 0; w2 < n_tw; ++w2) {
+                    const int nd = __popc(Lt.ballot[w2][0]), ns = __popc(Lt.ballot[w2][1]);
+                    if (w2 < warp) { dense_before += nd; scat_before += ns; }
+                    n_dense += nd;
+                    n_scat += ns;
+                }
+            }
+            if (len > 0) {
+                const int pos = kind == kKindDense ? dense_before : n_dense + scat_before;
+                Lt.lo[pos] = lo;
+                Lt.lenkind[pos] = len | (kind << 24);
+                Lt.w[pos] = S.w[t];
+            }
+            if (t == 0) { Lt.n = n_dense + n_scat; Lt.n_dense = n_dense; }
+        }
+        __syncthreads();        // list + zeroed accumulators visible
+        o0 = o1;
+        o1 = o2;
+
+        // ---- dense rows: fp32 registers, every thread its own docs
+        float4 racc[kChunks];
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) racc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int n_active = Lt.n, n_dense = Lt.n_dense;
+        for (int j = 0; j < n_dense; ++j) {
+            const float jw = Lt.w[j];
+            const float* __restrict__ src = dense_val + Lt.lo[j];
+#pragma unroll
+            for (int c = 0; c < kChunks; ++c) {
+                const int i = (c * T + t) * 4;
+                if (i < tile_docs) {
+                    const float4 a = __ldg(reinterpret_cast<const float4*>(src + i));
+                    racc[c].x = __fmaf_rn(a.x, jw, racc[c].x); racc[c].y = __fmaf_rn(a.y, jw, racc[c].y);
+                    racc[c].z = __fmaf_rn(a.z, jw, racc[c].z); racc[c].w = __fmaf_rn(a.w, jw, racc[c].w);
+                }
+            }
+        }
+        // ---- scatter terms: warp w takes terms w, w + n_warps, ...; integer atomics, no barrier between terms
+        for (int j = n_dense + warp; j < n_active; j += n_warps) {
+            const int jlk = Lt.lenkind[j];
+            const int jlen = jlk & 0xffffff;
+            const float jw = Lt.w[j] * kFxScale;
+            const long long jlo = Lt.lo[j];
+            if ((jlk >> 24) == kKindTiled) {
+                const uint16_t* __restrict__ op = A.ix.tiled_off + jlo;
+                const float* __restrict__ vp = tiled_val + jlo;
+                for (int i = 4 * lane; i < jlen; i += 128) {
+                    const uint2 o = __ldg(reinterpret_cast<const uint2*>(op + i));
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(vp + i));
+                    atomicAdd(&fx[o.x & 0xffffu], __float2int_rn(v.x * jw));
+                    atomicAdd(&fx[o.x >> 16], __float2int_rn(v.y * jw));
+                    atomicAdd(&fx[o.y & 0xffffu], __float2int_rn(v.z * jw));
+                    atomicAdd(&fx[o.y >> 16], __float2int_rn(v.w * jw));
+                }
+            } else {
+                const int32_t* __restrict__ dj = A.ix.post_doc + jlo;
+                const float* __restrict__ vj = short_val + jlo;
+                for (int p = lane; p < jlen; p += 32) {
+                    const unsigned o = (unsigned)(__ldg(dj + p) - dl);
+                    if (o < (unsigned)tile_docs) atomicAdd(&fx[o], __float2int_rn(__ldg(vj + p) * jw));
+                }
+            }
+        }
+        __syncthreads();        // every term's adds have landed
+
+        // ---- scan: registers (dense part) + this thread's own fixed-point slots
+        const int e_lo = MODE == 1 ? 0 : (int)(max(d_lo, A.r_lo) - d_lo);
+        const int e_hi = MODE == 1 ? (int)(d_hi - d_lo) : (int)(min(d_hi, A.r_hi) - d_lo);
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) {
+            const int i0 = (c * T + t) * 4;
+            const int4 f = *reinterpret_cast<const int4*>(fx + i0);
+            const float v[4] = {racc[c].x + (float)f.x * kFxInv, racc[c].y + (float)f.y * kFxInv,
+                                racc[c].z + (float)f.z * kFxInv, racc[c].w + (float)f.w * kFxInv};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float sc = v[u];
+                const bool inside = i0 + u >= e_lo && i0 + u < e_hi;
+                if (MODE == 1) {
+                    if (inside) A.out_full[(size_t)q * A.ix.n_docs + d_lo + i0 + u] = sc;
+                } else {
+                    const bool want = A.sign_mode > 0 ? (sc > lim) : (sc < 0.0f && sc > lim);
+                    if (want && inside) cand_append<float>(A.st, q, sc, (int32_t)(d_lo + i0 + u));
+                }
+            }
+        }
+    }
+}
+
+static bool splade_fixed_point_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("FZ_SPLADE_FIXED");
+        on = (e && e[0] == '1') ? 1 : 0;
+    }
+    return on == 1;
+}
+
 // Queries with fewer than k positive-score docs: append zero-score docs in ascending doc-id order
 // (the reference ranks every document; unmatched ones score exactly 0.0 and tie by index, bm25.py:103-105).
 template <typename AccT>
@@ -467,6 +640,8 @@ static int set_smem_attrs() {
         FZ_CUDA(cudaFuncSetAttribute(sparse_tile_kernel<AccT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         FZ_CUDA(cudaFuncSetAttribute(sparse_tile_kernel<AccT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         FZ_CUDA(cudaFuncSetAttribute(sparse_zero_fill_kernel<AccT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        if (std::is_same<AccT, float>::value)
+            FZ_CUDA(cudaFuncSetAttribute(sparse_tile_fx_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         done = true;
     }
     return FZ_OK;
@@ -526,7 +701,12 @@ static int sparse_topk(const fz_postings_t* ix, const int32_t* q_ptr, const int3
             const long long blocks = (long long)(ceil_div(A.tile_hi, kGroupTiles) - A.group_lo) * n_queries;
             FZ_REQUIRE(blocks < (1ll << 31), "grid too large");
             ProfScope prof(sizeof(AccT) == 8 ? "sparse_tile_f64" : "sparse_tile_f32", stream);
-            sparse_tile_kernel<AccT, 0><<<(unsigned)blocks, threads, smem, stream>>>(A);
+            if constexpr (std::is_same<AccT, float>::value) {
+                if (splade_fixed_point_enabled()) sparse_tile_fx_kernel<0><<<(unsigned)blocks, threads, smem, stream>>>(A);
+                else sparse_tile_kernel<AccT, 0><<<(unsigned)blocks, threads, smem, stream>>>(A);
+            } else {
+                sparse_tile_kernel<AccT, 0><<<(unsigned)blocks, threads, smem, stream>>>(A);
+            }
         }
         FZ_LAUNCH_CHECK();
         const bool last = hi >= SN;
