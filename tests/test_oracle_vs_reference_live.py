@@ -117,3 +117,24 @@ def test_metrics_oracle_equals_reference_on_random_rankings(seed):
     assert set(got) == set(want)
     for name in got:
         assert got[name] == pytest.approx(float(want[name]), abs=1e-12), name
+
+
+@pytest.mark.parametrize("sim", ["cos_sim", "dot"])
+def test_dense_oracle_equals_reference_search(sim):
+    """oracle/dense.py::semantic_search against the verbatim BaseModel.search (splade/base.py:199-251) with injected
+    embeddings, several query / doc chunks, an exact duplicate row."""
+    from oracle import dense as odense
+    g = torch.Generator().manual_seed(13)
+    q, d = torch.randn((9, 48), generator=g), torch.randn((2500, 48), generator=g)
+    d[100] = d[40]
+    m = ref_loader.make_injected_searcher(sim, q, d)
+    res = _quiet(m.search, ["x"] * 9, ["y"] * 2500, query_chunk_size=4, doc_chunk_size=700, topk=30)
+    mine = odense.semantic_search(q, d, 30, sim, query_chunk_size=4, corpus_chunk_size=700, key="doc_id")
+    for qi in range(9):
+        want_s = [x["score"] for x in res[qi]]
+        got_s = [x["score"] for x in mine[qi]]
+        assert got_s == want_s
+        # ids: equal outside exact-tie groups (the reference's order inside a tie group is arbitrary, SURVEY 8c)
+        want_i, got_i = [x["doc_id"] for x in res[qi]], [x["doc_id"] for x in mine[qi]]
+        for s in set(want_s):
+            assert {i for i, v in zip(want_i, want_s) if v == s} == {i for i, v in zip(got_i, got_s) if v == s}
