@@ -341,6 +341,21 @@ __global__ void __launch_bounds__(kMaxSparseThreads) sparse_tile_kernel(const Sp
         accumulate_tile<AccT, false>(A, tile, d_lo, acc, S, L[tile & 1], o0, o1, racc);
         o0 = o1;
         o1 = o2;
+#ifdef FZ_PREFETCH_SCATTER
+        // EXPERIMENTAL (build with FZ_PREFETCH_SCATTER=1, compiled out by default, not yet measured): pull the head of the
+        // NEXT tile's scatter segments into L1 while this tile is scanned.  A scatter phase waits for one L2 round trip to
+        // move a median of 23 (BM25) / 32 (SPLADE) postings; the term-holding lanes know the segment bounds one tile
+        // ahead, and a prefetch needs no register.
+        // fp64 (BM25) only: the fp32 kernel went from 40 to 48 registers with it (12 -> 10 CTAs per SM)
+        if (std::is_same<AccT, double>::value && tile + 1 < t_end && threadIdx.x < max(S.n, 1) &&
+            S.kind[threadIdx.x] == kKindTiled && o1 > o0) {
+            const long long p = S.base[threadIdx.x] + o0;
+            const char* vp = reinterpret_cast<const char*>(reinterpret_cast<const AccT*>(A.ix.tiled_val) + p);
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(A.ix.tiled_off + p));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(vp));
+            if ((o1 - o0) * sizeof(AccT) > 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(vp + 128));
+        }
+#endif
         // every thread scans its own docs in registers; survivors are rare once tau has risen
         // (a tile that straddles a round boundary is accumulated by both rounds and emitted once: [e_lo, e_hi))
         const int e_lo = MODE == 1 ? 0 : (int)(max(d_lo, A.r_lo) - d_lo);
