@@ -328,7 +328,7 @@ def main():
         qp, qt, qw = make_splade(nq, 24, 2, 64, 312, dev)
         q.sp_ptr, q.sp_term, q.sp_weight = sparse_queries(qp, qt, qw, "cos_sim", dev)
         ptr_h, term_h = q.sp_ptr.cpu().numpy(), q.sp_term.cpu().numpy()
-        df_loc = np.diff(sparse.term_ptr.cpu().numpy())
+        df_loc = torch.bincount(sparse.doc_post[:, 0].long(), minlength=SPLADE_VOCAB).cpu().numpy()
         algo["splade_bytes"] = float(sum(df_loc[term_h[ptr_h[i]:ptr_h[i + 1]]].sum() for i in range(nq)) * 8 + nq * TOP_K * 8)
         algo["splade_union_bytes"] = float(df_loc[np.unique(term_h[term_h >= 0])].sum()) * 8 + nq * TOP_K * 8
         algo["splade_index_bytes"] = sparse.nbytes()

@@ -10,11 +10,12 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libfusion_b200.so")
 
-FZ_STATUS_OVERFLOW, FZ_STATUS_NEED_ZERO, FZ_STATUS_NEED_NEG = 1, 2, 4
+FZ_STATUS_OVERFLOW, FZ_STATUS_NEED_ZERO, FZ_STATUS_NEED_NEG, FZ_STATUS_FALLBACK = 1, 2, 4, 8
 FUSE_METHODS = {"bcf": 0, "rrf": 1, "nsf": 2}
 FUSE_NORMS = {None: 0, "none": 0, "min-max": 1, "z-score": 2, "arctan": 3, "percentile-rank": 4,
               "normal-curve-equivalent": 5, "identity-f32": 6}
 LEX_TFIDF, LEX_BM25 = 0, 1
+ABI_VERSION = 2         # FZ_ABI_VERSION
 
 
 class FusionB200Error(RuntimeError):
@@ -28,6 +29,12 @@ class Postings(C.Structure):
                 ("tiled_off", C.c_void_p), ("tiled_val", C.c_void_p), ("dense_val", C.c_void_p),
                 ("dense_stride", C.c_int64), ("n_terms", C.c_int32), ("n_tiled", C.c_int32), ("n_dense", C.c_int32),
                 ("tile_docs", C.c_int32), ("n_tiles", C.c_int32), ("n_coarse", C.c_int32), ("n_docs", C.c_int64)]
+
+
+class SpladeHead(C.Structure):
+    """mirror of fz_splade_head_t"""
+    _fields_ = [("head_bf16", C.c_void_p), ("term_head", C.c_void_p), ("term_max", C.c_void_p), ("doc_ptr", C.c_void_p),
+                ("doc_post", C.c_void_p), ("head_dim", C.c_int32), ("n_terms", C.c_int32), ("n_docs", C.c_int64)]
 
 
 SHARD_HOOK = C.CFUNCTYPE(C.c_int, C.c_void_p)      # fz_shard_hook_t
@@ -71,6 +78,8 @@ SIGNATURES = {
     "fz_sparse_topk_f32": (_i, [_p, _p, _p, _p, _i, _i, _i64, _i, _i, _i, _p, _p, _p, _p, _sz, _p, _p]),
     "fz_sparse_scores_f64": (_i, [_p, _p, _p, _i, _p, _p]),
     "fz_sparse_scores_f32": (_i, [_p, _p, _p, _p, _i, _p, _p]),
+    "fz_splade_topk_workspace_bytes": (_sz, [_i, _i, _i, _i, _i64]),
+    "fz_splade_topk": (_i, [_p, _p, _p, _p, _p, _i, _i, _i64, _i, _i, _p, _p, _p, _p, _sz, _p, _p]),
     "fz_dense_topk_workspace_bytes": (_sz, [_i, _i, _i]),
     "fz_dense_topk": (_i, [_p, _p, _p, _p, _i, _i64, _i, _i, _f, _i64, _i, _i, _p, _p, _p, _p, _sz, _p]),
     "fz_dense_topk_filter": (_i, [_p, _p, _i, _i64, _i, _i, _f, _i64, _i, _i, _i, _p, _p, _p, _sz, _p, _p]),
@@ -97,7 +106,7 @@ def load() -> C.CDLL:
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args
-        if lib.fz_abi_version() != 1:
+        if lib.fz_abi_version() != ABI_VERSION:
             raise FusionB200Error("libfusion_b200.so ABI version mismatch - rebuild")
         _lib = lib
     return _lib

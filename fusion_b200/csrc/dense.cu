@@ -12,17 +12,9 @@
 // Replaces: sentence_transformers.util.semantic_search (src/retrievers/hybrid.py:103),
 // BaseModel.search (src/retrievers/splade/base.py:199-251), compute_metrices scoring loop
 // (src/utils/sentence_transformers.py:334-364).
-#include "common.cuh"
-#include "ptx.cuh"
-#include "topk_state.cuh"
-
-#include <cuda.h>
-#include <cuda_bf16.h>
-#include <limits>
+#include "filter_gemm.cuh"
 
 namespace fz {
-
-extern void* g_debug_stats;
 
 // ----------------------------------------------------------------------------------- tensor maps
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -55,251 +47,6 @@ int make_bf16_tile_map(CUtensorMap* map, const void* base, uint64_t rows, uint64
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     FZ_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return FZ_OK;
-}
-
-// ----------------------------------------------------------------------------------- filter GEMM
-constexpr int kBM = 128;          // queries per tile  (UMMA M)
-constexpr int kBN = 256;          // docs per tile     (UMMA N)
-constexpr int kBK = 64;           // bf16 elements per k-block = one 128-byte swizzle row
-constexpr int kStages = 4;
-constexpr int kABytes = kBM * kBK * 2;   // 16 KB
-constexpr int kBBytes = kBN * kBK * 2;   // 32 KB
-constexpr int kStageBytes = kABytes + kBBytes;
-constexpr int kGemmThreads = 384;        // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps 4-7 / 8-11 two epilogue teams
-constexpr int kTmemCols = 512;           // two 256-column fp32 accumulators
-constexpr size_t kGemmSmem = (size_t)kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
-
-struct GemmArgs {
-    int n_queries;
-    long long r_lo, r_hi;    // doc rows of this round
-    int num_k_blocks;
-    int m_tiles, n_tiles;
-    CandState<float> st;
-    unsigned long long* stats;   // optional [gridDim.x, 8] cycle counters (fz_debug_set_stats)
-};
-
-// CTA pairs (cluster of 2, adjacent query tiles, same doc tile): each CTA fetches HALF of the doc tile and multicasts it
-// to both, so the pair moves 16 + 16 KB per k-block and CTA instead of 16 + 32 KB.  The kernel is bound by L2 -> SM
-// operand traffic (profiles/), and 55 query tiles asking L2 for the same doc tile at once also miss together.
-constexpr int kPair = 2;
-__global__ void __cluster_dims__(kPair, 1, 1) __launch_bounds__(kGemmThreads, 1)
-dense_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_d,
-                    const GemmArgs G) {
-    extern __shared__ unsigned char smem_dyn[];
-    // 1024-byte alignment: required by the 128-byte swizzle atoms the UMMA descriptors assume
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * kStageBytes);
-    uint64_t* full_bar = bars;                     // [kStages]  TMA -> MMA
-    uint64_t* empty_bar = bars + kStages;          // [kStages]  MMA -> TMA
-    uint64_t* tfull_bar = bars + 2 * kStages;      // [2]        MMA -> epilogue
-    uint64_t* tempty_bar = bars + 2 * kStages + 2; // [2]        epilogue -> MMA
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // tile schedule: the cluster walks (doc tile, pair of query tiles); this CTA takes query tile 2 * pair + rank
-    const int crank = (int)ptx::cluster_ctarank();
-    const int cluster_id = blockIdx.x / kPair, n_clusters = gridDim.x / kPair;
-    const int m_pairs = (G.m_tiles + kPair - 1) / kPair;
-    const int total_tiles = m_pairs * G.n_tiles;     // per cluster
-
-    if (warp == 0 && lane == 0) {
-        ptx::prefetch_tensormap(&tmap_q);
-        ptx::prefetch_tensormap(&tmap_d);
-    }
-    if (warp == 1 && lane == 0) {
-        for (int i = 0; i < kStages; ++i) {
-            ptx::mbar_init(&full_bar[i], 1);
-            ptx::mbar_init(&empty_bar[i], kPair);       // both CTAs of the pair must have consumed a multicast stage
-        }
-        for (int i = 0; i < 2; ++i) {
-            ptx::mbar_init(&tfull_bar[i], 1);
-            ptx::mbar_init(&tempty_bar[i], 4);
-        }
-        ptx::fence_barrier_init();
-    }
-    if (warp == 2) {
-        ptx::tmem_alloc(tmem_slot, kTmemCols);
-        ptx::tmem_relinquish();
-    }
-    ptx::tc_fence_before();
-    __syncthreads();
-    ptx::cluster_sync();                 // the partner's barriers exist before anything is multicast to them
-    ptx::tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        // ================================ TMA producer (one elected lane) ================================
-        if (ptx::elect_one()) {
-            int stage = 0;
-            uint32_t phase = 0;
-            long long st_wait_empty = 0;
-            for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
-                const int n_t = tile / m_pairs, m_t = (tile - n_t * m_pairs) * kPair + crank;
-                const int q0 = m_t * kBM;       // may lie past the last query (odd tile count): TMA zero-fills
-                const long long d0 = G.r_lo + (long long)n_t * kBN;
-                for (int kb = 0; kb < G.num_k_blocks; ++kb) {
-                    const long long t0 = FZ_CLOCK();
-                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-                    st_wait_empty += FZ_CLOCK() - t0;
-                    unsigned char* sa = smem + (size_t)stage * kStageBytes;
-                    ptx::mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);     // own queries + both halves of the docs
-                    ptx::tma_load_2d(sa, &tmap_q, &full_bar[stage], kb * kBK, q0);
-                    ptx::tma_load_2d_multicast(sa + kABytes + crank * (kBBytes / kPair), &tmap_d, &full_bar[stage], kb * kBK,
-                                               (int32_t)(d0 + crank * (kBN / kPair)), (uint16_t)((1u << kPair) - 1));
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
-                }
-            }
-            if (G.stats) G.stats[blockIdx.x * 8 + 0] += (unsigned long long)st_wait_empty;
-        }
-    } else if (warp == 1) {
-        // ================================ MMA issuer (one elected lane) ===================================
-        if (ptx::elect_one()) {
-            const uint32_t idesc = ptx::make_idesc_bf16(kBM, kBN);
-            int stage = 0;
-            uint32_t phase = 0;
-            int it = 0;
-            long long st_wait_tempty = 0, st_wait_full = 0, st_issue = 0;
-            for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++it) {
-                const int buf = it & 1;
-                const long long t0 = FZ_CLOCK();
-                ptx::mbar_wait(&tempty_bar[buf], ((it >> 1) & 1) ^ 1);   // epilogue drained this accumulator
-                st_wait_tempty += FZ_CLOCK() - t0;
-                ptx::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)buf * kBN;
-                for (int kb = 0; kb < G.num_k_blocks; ++kb) {
-                    const long long t1 = FZ_CLOCK();
-                    ptx::mbar_wait(&full_bar[stage], phase);
-                    const long long t2 = FZ_CLOCK();
-                    st_wait_full += t2 - t1;
-                    ptx::tc_fence_after();
-                    const uint32_t sa = ptx::smem_u32(smem + (size_t)stage * kStageBytes);
-                    const uint32_t sb = sa + kABytes;
-#pragma unroll
-                    for (int k = 0; k < kBK / 16; ++k) {
-                        const uint64_t da = ptx::make_smem_desc_sw128(sa + k * 32);
-                        const uint64_t db = ptx::make_smem_desc_sw128(sb + k * 32);
-                        ptx::mma_bf16_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
-                    }
-                    // the stage is reusable once BOTH CTAs' MMAs on it have retired (either producer refills both copies)
-                    ptx::mma_commit_multicast(&empty_bar[stage], (uint16_t)((1u << kPair) - 1));
-                    st_issue += FZ_CLOCK() - t2;
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
-                }
-                ptx::mma_commit(&tfull_bar[buf]);           // accumulator complete
-            }
-            if (G.stats) {
-                G.stats[blockIdx.x * 8 + 1] += (unsigned long long)st_wait_tempty;
-                G.stats[blockIdx.x * 8 + 2] += (unsigned long long)st_wait_full;
-                G.stats[blockIdx.x * 8 + 3] += (unsigned long long)st_issue;
-            }
-        }
-    } else if (warp >= 4) {
-        // ================================ epilogue: TMEM -> threshold filter -> candidate append ==========
-        // Two teams of four warps: team t owns accumulator buffer t, i.e. every other tile of this CTA, so the candidate
-        // appends of one tile (an atomic round trip per thread) overlap the read-back of the next.
-        const int ew = (warp - 4) & 3;                      // == warp % 4: the TMEM lane quarter this warp may read
-        const int team = (warp - 4) >> 2;
-        int it = team;
-        long long st_wait_tfull = 0, st_pass2 = 0, st_pass2_n = 0;
-        const long long st_begin = FZ_CLOCK();
-        // Every global load on this path is issued one tile ahead: under a saturated memory system a demand load
-        // takes thousands of cycles and would otherwise sit between "accumulator ready" and "accumulator released".
-        auto tau_of = [&](int tile) {
-            if (tile >= total_tiles) return std::numeric_limits<float>::infinity();
-            const int n_t = tile / m_pairs, m_t = (tile - n_t * m_pairs) * kPair + crank;
-            const int q = m_t * kBM + ew * 32 + lane;
-            return q < G.n_queries ? G.st.tau[q] : std::numeric_limits<float>::infinity();
-        };
-        float tau_next = tau_of(cluster_id + team * n_clusters);
-        for (int tile = cluster_id + team * n_clusters; tile < total_tiles; tile += 2 * n_clusters, it += 2) {
-            const int n_t = tile / m_pairs, m_t = (tile - n_t * m_pairs) * kPair + crank;
-            const int buf = it & 1;
-            const int q = m_t * kBM + ew * 32 + lane;
-            const long long d0 = G.r_lo + (long long)n_t * kBN;
-            const int limit = (int)min((long long)kBN, G.r_hi - d0);
-            const float tau = tau_next;
-            tau_next = tau_of(tile + 2 * n_clusters);
-            const long long t0 = FZ_CLOCK();
-            ptx::mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
-            st_wait_tfull += FZ_CLOCK() - t0;
-            ptx::tc_fence_after();
-            const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)buf * kBN;
-            // Pass 1: each 32-column chunk is reduced with a max TREE (no dependent chain) while the next chunk's
-            // tcgen05.ld is already in flight; only a chunk whose maximum beats tau pays for the compare mask.
-            uint32_t ra[32], rb[32];
-            uint32_t flags = 0;
-            int total = 0;
-            ptx::tmem_ld_32x32(t_row, ra);
-#pragma unroll
-            for (int c = 0; c < kBN / 32; ++c) {
-                uint32_t(&cur)[32] = (c & 1) ? rb : ra;
-                ptx::tmem_ld_wait(cur);
-                if (c + 1 < kBN / 32) ptx::tmem_ld_32x32(t_row + (c + 1) * 32, (c & 1) ? ra : rb);
-                float m8[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    m8[j] = fmaxf(fmaxf(__uint_as_float(cur[j]), __uint_as_float(cur[j + 8])),
-                                  fmaxf(__uint_as_float(cur[j + 16]), __uint_as_float(cur[j + 24])));
-                const float mx = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])),
-                                       fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
-                if (mx > tau) {
-                    uint32_t mask = 0;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (__uint_as_float(cur[j]) > tau && c * 32 + j < limit) mask |= 1u << j;
-                    if (mask) {
-                        flags |= 1u << c;
-                        total += __popc(mask);
-                    }
-                }
-            }
-            // Pass 2: one atomic per thread and tile reserves the slots and the flagged chunks are read again.
-            // tcgen05.ld is warp-collective, so the chunk loop runs over the warp-wide union of the flags.
-            // (Parking the survivors in shared memory to release the accumulator before the atomic round trip was
-            // measured SLOWER: the kernel is bound by L2 -> SM operand traffic, and a team cannot start its next tile
-            // before its appends have drained anyway.)
-            const uint32_t wflags = __reduce_or_sync(0xffffffffu, flags);
-            const long long tp2 = FZ_CLOCK();
-            if (wflags) {
-                int base = total > 0 ? atomicAdd(&G.st.cnt[q], total) : 0;
-                const size_t off = (size_t)q * G.st.cap;
-#pragma unroll 1
-                for (int c = 0; c < kBN / 32; ++c) {
-                    if (!(wflags & (1u << c))) continue;
-                    ptx::tmem_ld_32x32(t_row + c * 32, ra);
-                    ptx::tmem_ld_wait(ra);
-                    if (flags & (1u << c)) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float v = __uint_as_float(ra[j]);
-                            if (v > tau && c * 32 + j < limit) {
-                                if (base < G.st.cap) {
-                                    G.st.score[off + base] = v;
-                                    G.st.id[off + base] = (int32_t)(d0 + c * 32 + j);
-                                }
-                                ++base;
-                            }
-                        }
-                    }
-                }
-                st_pass2 += FZ_CLOCK() - tp2;
-                ++st_pass2_n;
-            }
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&tempty_bar[buf]);
-        }
-        if (G.stats && ew == 0 && lane == 0 && team == 0) {
-            G.stats[blockIdx.x * 8 + 4] += (unsigned long long)st_wait_tfull;
-            G.stats[blockIdx.x * 8 + 5] += (unsigned long long)(FZ_CLOCK() - st_begin);
-            G.stats[blockIdx.x * 8 + 6] += (unsigned long long)st_pass2;
-            G.stats[blockIdx.x * 8 + 7] += (unsigned long long)st_pass2_n;
-        }
-    }
-    ptx::tc_fence_before();
-    __syncthreads();
-    ptx::cluster_sync();                 // no CTA leaves while its partner may still multicast into it
-    if (warp == 2) ptx::tmem_dealloc(tmem_base, kTmemCols);
 }
 
 // ----------------------------------------------------------------------------------- fp32 rescoring
@@ -427,7 +174,7 @@ static int dense_filter_phase(const void* q_bf16, const void* d_bf16, bool exact
     if (rc) return rc;
     static bool attr = false;
     if (!attr) {
-        FZ_CUDA(cudaFuncSetAttribute(dense_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
+        FZ_CUDA(cudaFuncSetAttribute(filter_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
         attr = true;
     }
     GemmArgs G;
@@ -452,7 +199,7 @@ static int dense_filter_phase(const void* q_bf16, const void* d_bf16, bool exact
             const int max_clusters = num_sms() / kPair;
             const int grid = kPair * (int)(pair_tiles < max_clusters ? pair_tiles : max_clusters);
             ProfScope prof("dense_filter_gemm", stream);
-            dense_filter_kernel<<<grid, kGemmThreads, kGemmSmem, stream>>>(tmap_q, tmap_d, G);
+            filter_gemm_kernel<false><<<grid, kGemmThreads, kGemmSmem, stream>>>(tmap_q, tmap_d, G);
         }
         FZ_LAUNCH_CHECK();
         const bool last = hi >= SN;

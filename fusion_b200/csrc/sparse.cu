@@ -11,6 +11,7 @@
 // evaluated once at index time with the same operation order and no FMA contraction (fz_lexical_impacts).
 #include "common.cuh"
 #include "topk_state.cuh"
+#include "splade_internal.cuh"
 
 #include <limits>
 
@@ -552,6 +553,178 @@ static bool splade_fixed_point_enabled() {
         on = (e && e[0] == '1') ? 1 : 0;
     }
     return on == 1;
+}
+
+template <typename AccT> static int check_index(const fz_postings_t* ix);
+
+// ------------------------------------------------------------------------------------ SPLADE tail codes (splade.cu)
+// The SPLADE pipeline scores the HEAD terms (the ~200 most frequent ones: 95+ % of all (query term, posting) pairs) on the
+// tensor cores (filter_gemm.cuh) and only needs an UPPER BOUND of the remaining tail sum per (query, doc) to decide which
+// docs can still reach the top-k; the survivors are rescored exactly.  This kernel produces that bound: the tail terms'
+// postings are scattered into fixed-point shared-memory accumulators (integer atomics: native, commutative, every addend
+// rounded up), one warp per term and no barrier between terms, and every doc's sum is rounded up into a 4-bit code
+// (filter_gemm.cuh: kCodeBase) written where the GEMM epilogue reads it: 16 bytes per (query, 32-doc chunk).
+constexpr float kTailScale = 67108864.0f;         // 2^26 fixed point of (tail * g) <= kCodeTop
+constexpr uint32_t kTailCodeBase = 0x3C000000u;   // == kCodeBase (filter_gemm.cuh)
+
+__global__ void __launch_bounds__(kMaxSparseThreads) tail_codes_kernel(const TailCodeArgs T, const SparseArgs<float> A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int* fx = reinterpret_cast<int*>(smem_raw);         // [tile_docs + 4], slot tile_docs = dump of the padding postings
+    __shared__ TermStatic S;
+    __shared__ TermListFx L[2];
+    const float* __restrict__ short_val = reinterpret_cast<const float*>(A.ix.post_val);
+    const float* __restrict__ tiled_val = reinterpret_cast<const float*>(A.ix.tiled_val);
+    const int NT = blockDim.x, t = threadIdx.x, lane = t & 31, warp = t >> 5, n_warps = NT >> 5;
+    const int tile_docs = A.ix.tile_docs;
+
+    const int group = A.group_lo + blockIdx.x / A.n_queries;
+    const int q = blockIdx.x % A.n_queries;
+    const int t_begin = max(group * kGroupTiles, A.tile_lo), t_end = min((group + 1) * kGroupTiles, A.tile_hi);
+    resolve_terms<float>(A, q, group, S);
+    const float gain = T.qparam[q].y * kTailScale;
+    const long long r_hi_pad = (T.r_hi + 255) / 256 * 256;
+    if (t == 0) fx[tile_docs] = 0;
+    __syncthreads();
+    uint32_t o0 = tile_offset<float>(A, S, t_begin), o1 = tile_offset<float>(A, S, t_begin + 1);
+    bool bad = false;
+    for (int tile = t_begin; tile < t_end; ++tile) {
+        const uint32_t o2 = tile + 1 < t_end ? tile_offset<float>(A, S, tile + 2) : 0;
+        const long long d_lo = (long long)tile * tile_docs;
+        const int dl = (int)d_lo;
+        TermListFx& Lt = L[tile & 1];
+        // ---- zero this thread's own accumulator slots (8 docs in each of 2 chunks), then the tile's term list
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const int i = (c * NT + t) * 8;
+            if (i < tile_docs) {
+                *reinterpret_cast<int4*>(fx + i) = make_int4(0, 0, 0, 0);
+                *reinterpret_cast<int4*>(fx + i + 4) = make_int4(0, 0, 0, 0);
+            }
+        }
+        const int n_tw = S.n <= 32 ? 1 : (S.n + 31) >> 5;
+        long long lo = 0;
+        int len = 0, kind = kKindNone;
+        unsigned bs = 0;
+        if (t < 32 * n_tw) {
+            kind = S.kind[t];
+            if (kind == kKindTiled) {
+                lo = S.base[t] + o0;
+                len = (int)(o1 - o0);
+            } else if (kind == kKindShort) {
+                lo = S.base[t];
+                len = S.aux[t];
+            }
+            bs = __ballot_sync(0xffffffffu, len > 0);
+            if (n_tw > 1 && lane == 0) Lt.ballot[warp][1] = bs;
+        }
+        if (n_tw > 1) __syncthreads();
+        if (t < 32 * n_tw) {
+            int before = __popc(bs & ((1u << lane) - 1)), n_act = __popc(bs);
+            if (n_tw > 1) {
+                n_act = 0;
+                for (int w2 = 0; w2 < n_tw; ++w2) {
+                    const int ns = __popc(Lt.ballot[w2][1]);
+                    if (w2 < warp) before += ns;
+                    n_act += ns;
+                }
+            }
+            if (len > 0) {
+                Lt.lo[before] = lo;
+                Lt.lenkind[before] = len | (kind << 24);
+                Lt.w[before] = S.w[t] * gain;
+            }
+            if (t == 0) Lt.n = n_act;
+        }
+        __syncthreads();        // list + zeroed accumulators visible
+        o0 = o1;
+        o1 = o2;
+
+        // ---- scatter: warp w takes terms w, w + n_warps, ...; integer atomics, no barrier between terms
+        const int n_active = Lt.n;
+        for (int j = warp; j < n_active; j += n_warps) {
+            const int jlk = Lt.lenkind[j];
+            const int jlen = jlk & 0xffffff;
+            const float jw = Lt.w[j];
+            const long long jlo = Lt.lo[j];
+            if ((jlk >> 24) == kKindTiled) {
+                const uint16_t* __restrict__ op = A.ix.tiled_off + jlo;
+                const float* __restrict__ vp = tiled_val + jlo;
+                for (int i = 4 * lane; i < jlen; i += 128) {
+                    const uint2 o = __ldg(reinterpret_cast<const uint2*>(op + i));
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(vp + i));
+                    atomicAdd(&fx[o.x & 0xffffu], __float2int_ru(v.x * jw));
+                    atomicAdd(&fx[o.x >> 16], __float2int_ru(v.y * jw));
+                    atomicAdd(&fx[o.y & 0xffffu], __float2int_ru(v.z * jw));
+                    atomicAdd(&fx[o.y >> 16], __float2int_ru(v.w * jw));
+                }
+            } else {
+                const int32_t* __restrict__ dj = A.ix.post_doc + jlo;
+                const float* __restrict__ vj = short_val + jlo;
+                for (int p = lane; p < jlen; p += 32) {
+                    const unsigned o = (unsigned)(__ldg(dj + p) - dl);
+                    if (o < (unsigned)tile_docs) atomicAdd(&fx[o], __float2int_ru(__ldg(vj + p) * jw));
+                }
+            }
+        }
+        __syncthreads();        // every term's adds have landed
+
+        // ---- encode: 8 docs -> one 32-bit word of codes, rounded up
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const int i = (c * NT + t) * 8;
+            const long long d = d_lo + i;
+            if (i < tile_docs && d >= T.r_lo && d < r_hi_pad) {
+                const int4 f0 = *reinterpret_cast<const int4*>(fx + i), f1 = *reinterpret_cast<const int4*>(fx + i + 4);
+                const int f[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+                uint32_t word = 0;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const float tv = __fadd_ru(__int2float_ru(f[u]) * (1.0f / kTailScale), 0.0078125f);
+                    uint32_t code = (__float_as_uint(tv) - kTailCodeBase + 0x3FFFFFu) >> 22;
+                    if (code > 15u || f[u] < 0) { bad = true; code = 15u; }
+                    word |= code << (4 * u);
+                }
+                const long long g8 = (d - T.r_lo) >> 3;
+                T.codes[(((g8 >> 5) * 8 + ((g8 >> 2) & 7)) * (long long)T.q_pad + q) * 4 + (g8 & 3)] = word;
+            }
+        }
+        // (the next tile's zeroing touches only this thread's own slots, which it has just read)
+    }
+    if (bad) atomicOr(&T.status[q], FZ_STATUS_FALLBACK);
+}
+
+int launch_tail_codes(const TailCodeArgs& T, cudaStream_t stream) {
+    const fz_postings_t* ix = &T.ix;
+    int rc = check_index<float>(ix);
+    if (rc) return rc;
+    FZ_REQUIRE(ix->tile_docs % 256 == 0 && ix->n_dense == 0, "tail index: tile_docs must be a multiple of 256, no dense rows");
+    FZ_REQUIRE(T.r_lo % 256 == 0 && T.r_hi > T.r_lo, "tail round must start on a multiple of 256");
+    static bool attr = false;
+    if (!attr) {
+        FZ_CUDA(cudaFuncSetAttribute(tail_codes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        attr = true;
+    }
+    SparseArgs<float> A;
+    memset(&A, 0, sizeof(A));
+    A.ix = *ix;
+    A.q_ptr = T.q_ptr;
+    A.q_term = T.q_term;
+    A.q_weight = T.q_weight;
+    A.n_queries = T.n_queries;
+    A.tile_lo = (int)(T.r_lo / ix->tile_docs);
+    A.tile_hi = (int)ceil_div<long long>(T.r_hi < ix->n_docs ? T.r_hi : ix->n_docs, ix->tile_docs);
+    if (A.tile_hi <= A.tile_lo) A.tile_hi = A.tile_lo + 1;
+    A.group_lo = A.tile_lo / kGroupTiles;
+    const long long blocks = (long long)(ceil_div(A.tile_hi, kGroupTiles) - A.group_lo) * T.n_queries;
+    FZ_REQUIRE(blocks < (1ll << 31), "grid too large");
+    int threads = (ix->tile_docs + 15) / 16;
+    threads = (threads + 31) / 32 * 32;
+    if (threads < kMaxTerms) threads = kMaxTerms;
+    FZ_REQUIRE(threads <= kMaxSparseThreads, "tail tile_docs=%d too large (max %d)", ix->tile_docs, 16 * kMaxSparseThreads);
+    ProfScope prof("splade_tail_codes", stream);
+    tail_codes_kernel<<<(unsigned)blocks, threads, ((size_t)ix->tile_docs + 4) * sizeof(int), stream>>>(T, A);
+    FZ_LAUNCH_CHECK();
+    return FZ_OK;
 }
 
 // Queries with fewer than k positive-score docs: append zero-score docs in ascending doc-id order

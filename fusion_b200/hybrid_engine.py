@@ -119,8 +119,8 @@ class HybridSearcher:
             s, i = self._timed("dpr", run_dense)
             out["dpr"] = self._timed("dpr_merge", lambda: self._merge(s, i))
         if self.sparse is not None:
-            s, i = self._timed("splade", lambda: ops.sparse_topk(self.sparse.view(), q.sp_ptr, q.sp_term, q.sp_weight,
-                                                                  self.k, self.sparse.doc_base, sync=self._sync.get("splade")))
+            s, i = self._timed("splade", lambda: self.sparse.topk(q.sp_ptr, q.sp_term, q.sp_weight, self.k,
+                                                                   sync=self._sync.get("splade")))
             out["splade"] = self._timed("splade_merge", lambda: self._merge(s, i))
         if self.lexical is not None:
             s, i = self._timed("bm25", lambda: ops.sparse_topk(self.lexical.view(), q.lex_ptr, q.lex_term, None, self.k,

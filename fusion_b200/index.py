@@ -235,37 +235,97 @@ class LexicalIndex:
                                          (self.term_ptr, self.post_doc, self.post_tf, self.doc_len))
 
 
+SP_HEAD_DIM = int(os.environ.get("FZ_SPLADE_HEAD", 192))           # head terms scored on the tensor cores (multiple of 64, <= 256)
+SP_TAIL_TILE_DOCS = int(os.environ.get("FZ_TILE_DOCS_TAIL", 8192))   # docs per fixed-point accumulator tile of the tail kernel
+
+
 class SparseIndex:
-    """Inverted index over sparse term-weight vectors (SPLADE): doc weights are L2-normalised at build time for
-    cos_sim, so a query is scored as sum_t (q_t/|q|) * (d_t/|d|) over the terms they share."""
+    """Index over sparse term-weight vectors (SPLADE): doc weights are L2-normalised at build time for cos_sim, so a
+    query is scored as sum_t (q_t/|q|) * (d_t/|d|) over the terms they share (hybrid.py:101-103 on dense [., V] vectors).
+
+    Two device forms are kept:
+      * the HEAD / TAIL split of ``fz_splade_topk`` (non-negative weights only): the ``head_dim`` most frequent terms as a
+        dense doc-major bf16 matrix (tensor-core operand), the other terms as an inverted index for the tail bound, and
+        the doc-major (term, weight) copy the survivors are rescored from exactly;
+      * the general three-form inverted index of ``fz_sparse_topk_f32`` / ``fz_sparse_scores_f32`` over ALL terms, built
+        lazily on first use (full-ranking mode, queries the fast path hands back, negative weights).
+    """
 
     def __init__(self, doc_ptr, doc_term, doc_weight, vocab_size: int, similarity: str = "cos_sim", device="cuda",
                  doc_base: int = 0, tile_docs: int = SP_TILE_DOCS, tiled_min: int | None = None,
-                 dense_frac: float = DENSE_FRAC):
+                 dense_frac: float = DENSE_FRAC, head_dim: int | None = None, tail_tile_docs: int | None = None):
         if similarity not in ("cos_sim", "dot"):
             raise FusionB200Error(f"unknown similarity {similarity!r}")
         self.similarity, self.vocab_size, self.doc_base, self.tile_docs = similarity, int(vocab_size), int(doc_base), int(tile_docs)
+        self.tiled_min, self.dense_frac = tiled_min, dense_frac
         self.device = torch.device(device)
-        doc_ptr = torch.as_tensor(doc_ptr, dtype=torch.int64, device=self.device)
-        term = torch.as_tensor(doc_term, device=self.device).to(torch.int64)
+        self.doc_ptr = torch.as_tensor(doc_ptr, dtype=torch.int64, device=self.device).contiguous()
+        term = torch.as_tensor(doc_term, device=self.device).to(torch.int32)
         w = torch.as_tensor(doc_weight, dtype=torch.float32, device=self.device)
-        self.n_docs = doc_ptr.numel() - 1
-        lens = doc_ptr[1:] - doc_ptr[:-1]
-        row = torch.repeat_interleave(torch.arange(self.n_docs, device=self.device), lens)
+        self.n_docs = self.doc_ptr.numel() - 1
+        lens = self.doc_ptr[1:] - self.doc_ptr[:-1]
+        row = torch.repeat_interleave(torch.arange(self.n_docs, device=self.device, dtype=torch.int32), lens)
         if similarity == "cos_sim":
             sq = torch.zeros(self.n_docs, dtype=torch.float32, device=self.device).index_add_(0, row, w * w)
-            w = w / torch.clamp(torch.sqrt(sq), min=1e-12)[row]
-        order, self.term_ptr, df = _term_major_csr(row, term, self.n_docs, self.vocab_size)
-        post_doc = row[order].to(torch.int32)
-        post_w = w[order].contiguous()
-        del row, w, order, term
-        self._view = build_postings(self.term_ptr, post_doc, post_w, self.n_docs, self.tile_docs, tiled_min, dense_frac)
+            w = w / torch.clamp(torch.sqrt(sq), min=1e-12)[row.long()]
+            del sq
+        # doc-major copy: (int32 term, float weight) pairs, 8 bytes per posting
+        self.doc_post = torch.stack([term, w.view(torch.int32)], dim=1).contiguous()
+        self.nonneg = bool((w >= 0).all()) if w.numel() else True
+        self._view = None
+        self.head = None
+        head_dim = SP_HEAD_DIM if head_dim is None else int(head_dim)
+        if self.nonneg and head_dim > 0 and self.n_docs > 0:
+            self._build_head_tail(row, term, w, head_dim, int(tail_tile_docs or SP_TAIL_TILE_DOCS))
+
+    def _build_head_tail(self, row, term, w, head_dim, tail_tile_docs):
+        dev, n, v = self.device, self.n_docs, self.vocab_size
+        if head_dim % 64 or not (64 <= head_dim <= 256):
+            raise FusionB200Error(f"head_dim={head_dim} must be 64, 128, 192 or 256")
+        df = torch.bincount(term.long(), minlength=v)
+        n_head = min(head_dim, int((df > 0).sum()))
+        head_terms = torch.topk(df, n_head).indices if n_head else torch.zeros(0, dtype=torch.int64, device=dev)
+        term_head = torch.full((v,), -1, dtype=torch.int32, device=dev)
+        term_head[head_terms] = torch.arange(n_head, dtype=torch.int32, device=dev)
+        term_max = torch.zeros(v, dtype=torch.float32, device=dev).scatter_reduce_(0, term.long(), w, "amax", include_self=True)
+        th = term_head[term.long()]
+        m = th >= 0
+        head = torch.zeros((n, head_dim), dtype=torch.bfloat16, device=dev)
+        head[row[m].long(), th[m].long()] = w[m].to(torch.bfloat16)
+        m = ~m
+        row_t, term_t, w_t = row[m], term[m], w[m]
+        del th, m
+        order, term_ptr_t, _ = _term_major_csr(row_t, term_t, n, v)
+        tail_tile_docs = max(256, min(tail_tile_docs, (n + 255) // 256 * 256))
+        tail = build_postings(term_ptr_t, row_t[order].to(torch.int32), w_t[order].contiguous(), n, tail_tile_docs,
+                              self.tiled_min, dense_frac=0.0)
+        self.head = ops.SpladeHeadView(head, term_head, term_max, self.doc_ptr, self.doc_post, tail, head_dim, v, n)
 
     def view(self) -> ops.PostingsView:
+        """The general inverted index over all terms (built on first use)."""
+        if self._view is None:
+            lens = self.doc_ptr[1:] - self.doc_ptr[:-1]
+            row = torch.repeat_interleave(torch.arange(self.n_docs, device=self.device), lens)
+            term = self.doc_post[:, 0].long()
+            w = self.doc_post[:, 1].contiguous().view(torch.float32)
+            order, self.term_ptr, _ = _term_major_csr(row, term, self.n_docs, self.vocab_size)
+            self._view = build_postings(self.term_ptr, row[order].to(torch.int32), w[order].contiguous(), self.n_docs,
+                                        self.tile_docs, self.tiled_min, self.dense_frac)
         return self._view
 
+    def topk(self, q_ptr, q_term, q_weight, k: int, cap: int = ops.DEFAULT_CAP, sync: "ops.ShardSync | None" = None):
+        """Top-k of one query batch: the head/tail pipeline when the index has one, else the general inverted index."""
+        if self.head is not None:
+            return ops.splade_topk(self, q_ptr, q_term, q_weight, k, self.doc_base, cap=cap, sync=sync)
+        return ops.sparse_topk(self.view(), q_ptr, q_term, q_weight, k, self.doc_base, cap=cap, sync=sync)
+
     def nbytes(self) -> int:
-        return self._view.nbytes() + self.term_ptr.numel() * 8
+        b = self.doc_ptr.numel() * 8 + self.doc_post.numel() * 4
+        if self.head is not None:
+            b += self.head.nbytes()
+        if self._view is not None:
+            b += self._view.nbytes() + self.term_ptr.numel() * 8
+        return b
 
 
 def sparse_queries(q_ptr, q_term, q_weight, similarity: str, device):

@@ -12,7 +12,7 @@ from dataclasses import dataclass
 import torch
 
 from . import _lib
-from ._lib import FZ_STATUS_NEED_NEG, FZ_STATUS_OVERFLOW, FusionB200Error, check
+from ._lib import FZ_STATUS_FALLBACK, FZ_STATUS_NEED_NEG, FZ_STATUS_OVERFLOW, FusionB200Error, check
 
 DEFAULT_CAP = 8192
 COARSE_TILES = 16          # FZ_COARSE_TILES
@@ -381,6 +381,71 @@ def sparse_topk(pv: PostingsView, q_ptr, q_term, q_weight, k: int, doc_base: int
             take = k_eff - have
             out_s[qi, have:] = s2[j, :take]
             out_i[qi, have:] = i2[j, :take]
+    return out_s, out_i
+
+
+@dataclass
+class SpladeHeadView:
+    """Device tensors of ``fz_splade_head_t`` + the tail-only inverted index (built by fusion_b200.index.SparseIndex)."""
+    head_bf16: torch.Tensor       # bf16 [N, head_dim]
+    term_head: torch.Tensor       # int32 [V]
+    term_max: torch.Tensor        # float32 [V]
+    doc_ptr: torch.Tensor         # int64 [N+1]
+    doc_post: torch.Tensor        # int32 [nnz, 2]: (term, weight bits)
+    tail: PostingsView            # tail terms only, no dense rows, tile_docs % 256 == 0
+    head_dim: int
+    n_terms: int
+    n_docs: int
+
+    def nbytes(self) -> int:
+        return self.tail.nbytes() + sum(t.numel() * t.element_size() for t in (self.head_bf16, self.term_head, self.term_max))
+
+    def c_struct(self) -> _lib.SpladeHead:
+        return _lib.SpladeHead(self.head_bf16.data_ptr(), self.term_head.data_ptr(), self.term_max.data_ptr(),
+                               self.doc_ptr.data_ptr(), self.doc_post.data_ptr(), self.head_dim, self.n_terms, self.n_docs)
+
+
+SPLADE_GROWTH = 3               # rounds grow 3x: a round emits the docs whose score UPPER BOUND beats the running k-th score
+SPLADE_MAX_ROUND_DOCS = 1 << 21    # bounds the code buffer: n_queries * max_round_docs / 2 bytes
+
+
+def splade_topk(index, q_ptr, q_term, q_weight, k: int, doc_base: int = 0, cap: int = DEFAULT_CAP,
+                growth: int = SPLADE_GROWTH, sync: ShardSync | None = None, max_round_docs: int = SPLADE_MAX_ROUND_DOCS):
+    """SPLADE top-k through ``fz_splade_topk``: head terms on the tensor cores, a 4-bit upper bound of the tail sum per
+    (query, doc), exact fp32 rescoring of the survivors.  ``index``: a ``fusion_b200.index.SparseIndex`` with a head/tail
+    split.  Same result contract as :func:`sparse_topk` (scores exact fp32 sparse dot products, score desc, ties by lower
+    doc id, zero-score docs fill up in doc-id order).  Queries the fast path hands back (negative weights, fewer than k
+    positive-score docs, candidate-buffer overflow) are re-run on the general inverted index - never with ``sync``."""
+    lib = _lib.load()
+    hv: SpladeHeadView = index.head
+    q_ptr = _req(q_ptr, torch.int32, "q_ptr")
+    q_term = _req(q_term, torch.int32, "q_term")
+    if q_weight is not None:
+        q_weight = _req(q_weight, torch.float32, "q_weight")
+    _check_query_lengths(q_ptr)
+    dev = hv.head_bf16.device
+    nq = q_ptr.numel() - 1
+    k_eff = min(k, hv.n_docs)
+    cap = max(cap, 2 * k_eff)
+    out_s = torch.empty((nq, k_eff), dtype=torch.float32, device=dev)
+    out_i = torch.empty((nq, k_eff), dtype=torch.int32, device=dev)
+    status = torch.empty((nq,), dtype=torch.int32, device=dev)
+    if nq == 0:
+        return out_s, out_i
+    round_docs = max(256, min(int(max_round_docs), (hv.n_docs + 255) // 256 * 256))
+    ws = _ws(lib.fz_splade_topk_workspace_bytes(nq, k_eff, cap, hv.head_dim, round_docs), dev)
+    sc = _SyncCall(sync, nq, torch.float32, dev, k)
+    tail, head = hv.tail.c_struct(), hv.c_struct()
+    rc = lib.fz_splade_topk(C.byref(tail), C.byref(head), _ptr(q_ptr), _ptr(q_term), _ptr(q_weight), nq, k_eff, doc_base, cap,
+                            growth, _ptr(out_s), _ptr(out_i), _ptr(status), _ptr(ws), ws.numel(), sc.ref(), _stream(out_s))
+    sc.reraise()
+    check(rc, "fz_splade_topk")
+    bad = (status & (FZ_STATUS_OVERFLOW | FZ_STATUS_FALLBACK)) != 0
+    if bool(bad.any()):
+        sel = torch.nonzero(bad).flatten()
+        p2, t2, w2 = _subset_queries(q_ptr, q_term, q_weight, sel)
+        s2, i2 = sparse_topk(index.view(), p2, t2, w2, k_eff, doc_base, cap=cap)
+        out_s[sel], out_i[sel] = s2, i2
     return out_s, out_i
 
 

@@ -141,7 +141,7 @@ class Ranker:
         k = min(top_k, index.n_docs)
         if k >= FULL_RANKING_MIN_K or 2 * k > ops.DEFAULT_CAP:
             return ops.rank_rows(ops.sparse_scores(index.view(), qp, qt, qw), k, 0)
-        return ops.sparse_topk(index.view(), qp, qt, qw, k)
+        return index.topk(qp, qt, qw, k)
 
     @staticmethod
     def multi_vector_search(queries: list[str], corpus: dict[int, str], model_name_or_path, output_dir: str = 'output',

@@ -26,7 +26,7 @@ extern "C" {
 #define FZ_ERR_CUDA (-2)
 #define FZ_ERR_UNSUPPORTED (-3)
 
-#define FZ_ABI_VERSION 1
+#define FZ_ABI_VERSION 2
 
 typedef void* fz_stream_t; /* cudaStream_t */
 
@@ -45,6 +45,8 @@ int fz_debug_set_stats(void* device_buffer);
 #define FZ_STATUS_OVERFLOW 1  /* candidate buffer overflowed: result for this query is NOT valid, re-run with growth=1 */
 #define FZ_STATUS_NEED_ZERO 2 /* fewer than k positive-score docs: zero-score docs were appended in doc-id order */
 #define FZ_STATUS_NEED_NEG 4  /* positives + zero-score docs < k: negative-score docs are missing from the tail */
+#define FZ_STATUS_FALLBACK 8  /* fz_splade_topk only: this query is outside the fast path's contract (negative weights, fewer than
+                                k positive-score docs, a tail sum outside the code range): re-run it with fz_sparse_topk_f32 */
 
 /* ------------------------------------------------------------------------------------------------------------
  * K5  k-way merge of per-shard / per-chunk top-k lists.
@@ -253,6 +255,41 @@ int fz_sparse_scores_f64(const fz_postings_t* index, const int32_t* q_ptr, const
                          double* out_scores, fz_stream_t stream);
 int fz_sparse_scores_f32(const fz_postings_t* index, const int32_t* q_ptr, const int32_t* q_term, const float* q_weight,
                          int n_queries, float* out_scores, fz_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * K2c  SPLADE top-k as head GEMM + tail bound + exact rescoring (non-negative weights: SPLADE activations are
+ * log1p(relu(.)) >= 0, src/retrievers/splade/splade.py:94).  Same contract as fz_sparse_topk_f32 - the dense [Q,V]x[V,N]
+ * cosine of src/retrievers/hybrid.py:101-103 / splade/base.py:186-251, scores in fp32 to 1e-5 - for the queries it can serve.
+ *
+ * A Zipfian vocabulary puts > 95 % of all (query term, posting) pairs into the ~200 most frequent terms.  Those HEAD terms
+ * are stored as a dense doc-major bf16 matrix and scored on the tensor cores (the K1 filter GEMM); the remaining TAIL terms
+ * keep the inverted index (fz_postings_t built from the tail terms only, no dense rows, tile_docs % 256 == 0), but their
+ * sum is only needed as an upper bound: a 4-bit code per (query, doc).  A doc whose head score + tail bound can still beat
+ * the query's running k-th EXACT score is appended to the candidate buffer and rescored exactly in fp32 from the doc-major
+ * CSR copy; between rounds cand_select tightens the threshold on exact scores.  The returned scores are the exact ones.
+ *   head_bf16 [n_docs, head_dim]: weight of head term j in doc d (bf16, row-major, head_dim % 64 == 0, 64..256)
+ *   term_head [n_terms]: head column of a term, -1 for tail terms;  term_max [n_terms]: max weight of the term in the shard
+ *   doc_ptr [n_docs + 1], doc_post [nnz] (int32 term, float weight) pairs: the doc-major copy, terms in any order
+ * Queries that leave the fast path's contract get FZ_STATUS_FALLBACK (or FZ_STATUS_OVERFLOW) in out_status and an
+ * unspecified row: the caller re-runs those with fz_sparse_topk_f32 on the full index.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct fz_splade_head {
+    const void* head_bf16;
+    const int32_t* term_head;
+    const float* term_max;
+    const int64_t* doc_ptr;
+    const void* doc_post;
+    int32_t head_dim;
+    int32_t n_terms;
+    int64_t n_docs;
+} fz_splade_head_t;
+
+/* max_round_docs bounds the code buffer (n_queries * max_round_docs / 2 bytes): rounds never span more documents */
+size_t fz_splade_topk_workspace_bytes(int n_queries, int k, int cap, int head_dim, int64_t max_round_docs);
+int fz_splade_topk(const fz_postings_t* tail_index, const fz_splade_head_t* head, const int32_t* q_ptr, const int32_t* q_term,
+                   const float* q_weight, int n_queries, int k, int64_t doc_base, int cap, int growth, float* out_scores,
+                   int32_t* out_ids, int32_t* out_status, void* ws, size_t ws_bytes,
+                   const fz_shard_sync_t* sync /* may be NULL */, fz_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * K1  dense exhaustive inner-product scoring with top-k fused into the tcgen05 GEMM epilogue.
