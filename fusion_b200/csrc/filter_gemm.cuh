@@ -209,7 +209,10 @@ filter_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
                 gh = p.x;
                 if (tau > 0.0f) {
                     const float t = fmaf(tau, p.y, kCodeB0);
-                    thr = t - t * 3.8e-6f;      // the fma below rounds (2^-24 relative): never lose a borderline doc
+                    // the fma below rounds (2^-24 relative): never lose a borderline doc.  Never below B0: a doc that
+                    // shares no term with the query (head 0, code 0; also the zero-filled rows past the last doc)
+                    // evaluates to exactly B0 and must not pass.
+                    thr = fmaxf(t - t * 3.8e-6f, kCodeB0);
                 } else {
                     thr = -std::numeric_limits<float>::infinity();
                 }
@@ -239,9 +242,63 @@ filter_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
             st_wait_tfull += FZ_CLOCK() - t0;
             ptx::tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)buf * kBN;
+            uint32_t ra[32], rb[32];
+            if constexpr (kCodes) {
+                // Branch-free: lanes are different queries, so "some lane of the warp has a survivor in this chunk" is the
+                // normal case and a warp-level slow path would run almost always.  Every element costs the decode (shift +
+                // LOP3), one FFMA and a compare folded into the survivor mask; no max tree, no second pass over TMEM.
+                uint32_t masks[kBN / 32];
+                const bool collect_all = !(tau > -std::numeric_limits<float>::infinity());   // no threshold yet (first rounds)
+                ptx::tmem_ld_32x32(t_row, ra);
+#pragma unroll
+                for (int c = 0; c < kBN / 32; ++c) {
+                    uint32_t(&cur)[32] = (c & 1) ? rb : ra;
+                    ptx::tmem_ld_wait(cur);
+                    if (c + 1 < kBN / 32) ptx::tmem_ld_32x32(t_row + (c + 1) * 32, (c & 1) ? ra : rb);
+                    const uint32_t w4[4] = {cw[c].x, cw[c].y, cw[c].z, cw[c].w};
+                    uint32_t mask = 0;
+                    if (!collect_all) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (fmaf(__uint_as_float(cur[j]), gh, code_decode(w4[j >> 3], j & 7)) > tau) mask |= 1u << j;
+                    } else {
+                        // every doc of the round that shares a term with the query (head != 0 or code != 0)
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if ((cur[j] != 0u || ((w4[j >> 3] >> (4 * (j & 7))) & 15u) != 0u) && c * 32 + j < limit) mask |= 1u << j;
+                    }
+                    masks[c] = mask;
+                }
+                // The survivors are rescored exactly afterwards, so only their doc ids are recorded: the accumulator is
+                // released BEFORE the slot-reserving atomic (its round trip is off the tensor pipe's critical path) and the
+                // append walks the set bits of the masks - work proportional to the survivors, not to the tile.
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&tempty_bar[buf]);
+                int total = 0;
+#pragma unroll
+                for (int c = 0; c < kBN / 32; ++c) total += __popc(masks[c]);
+                if (total > 0) {
+                    const long long tp2 = FZ_CLOCK();
+                    int base = atomicAdd(&G.st.cnt[q], total);
+                    int32_t* ids = G.st.id + (size_t)q * G.st.cap;
+#pragma unroll
+                    for (int c = 0; c < kBN / 32; ++c) {
+                        uint32_t m = masks[c];
+                        while (m) {
+                            const int j = __ffs(m) - 1;
+                            m &= m - 1;
+                            if (base < G.st.cap) ids[base] = (int32_t)((uint32_t)(d0 + c * 32 + j) | kPendingBit);
+                            ++base;
+                        }
+                    }
+                    st_pass2 += FZ_CLOCK() - tp2;
+                    ++st_pass2_n;
+                }
+                continue;
+            }
             // Pass 1: each 32-column chunk is reduced with a max TREE (no dependent chain) while the next chunk's
             // tcgen05.ld is already in flight; only a chunk whose maximum beats tau pays for the compare mask.
-            uint32_t ra[32], rb[32];
             uint32_t flags = 0;
             int total = 0;
             ptx::tmem_ld_32x32(t_row, ra);
@@ -250,39 +307,31 @@ filter_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
                 uint32_t(&cur)[32] = (c & 1) ? rb : ra;
                 ptx::tmem_ld_wait(cur);
                 if (c + 1 < kBN / 32) ptx::tmem_ld_32x32(t_row + (c + 1) * 32, (c & 1) ? ra : rb);
-                uint32_t w4[4] = {0, 0, 0, 0};
-                if constexpr (kCodes) { w4[0] = cw[c].x; w4[1] = cw[c].y; w4[2] = cw[c].z; w4[3] = cw[c].w; }
-                auto val = [&](int j) {
-                    if constexpr (kCodes) return fmaf(__uint_as_float(cur[j]), gh, code_decode(w4[j >> 3], j & 7));
-                    else return __uint_as_float(cur[j]);
-                };
                 float m8[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) m8[j] = fmaxf(fmaxf(val(j), val(j + 8)), fmaxf(val(j + 16), val(j + 24)));
+                for (int j = 0; j < 8; ++j)
+                    m8[j] = fmaxf(fmaxf(__uint_as_float(cur[j]), __uint_as_float(cur[j + 8])),
+                                  fmaxf(__uint_as_float(cur[j + 16]), __uint_as_float(cur[j + 24])));
                 const float mx = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])),
                                        fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
                 if (mx > tau) {
                     uint32_t mask = 0;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        bool hit = val(j) > tau && c * 32 + j < limit;
-                        // a doc that shares no term with the query (head 0, code 0) scores exactly 0: never a candidate
-                        if constexpr (kCodes) hit = hit && (cur[j] != 0u || ((w4[j >> 3] >> (4 * (j & 7))) & 15u) != 0u);
-                        if (hit) mask |= 1u << j;
-                    }
+                    for (int j = 0; j < 32; ++j)
+                        if (__uint_as_float(cur[j]) > tau && c * 32 + j < limit) mask |= 1u << j;
                     if (mask) {
                         flags |= 1u << c;
                         total += __popc(mask);
                     }
                 }
             }
+            const long long tp2 = FZ_CLOCK();
             // Pass 2: one atomic per thread and tile reserves the slots and the flagged chunks are read again.
             // tcgen05.ld is warp-collective, so the chunk loop runs over the warp-wide union of the flags.
             // (Parking the survivors in shared memory to release the accumulator before the atomic round trip was
             // measured SLOWER: the kernel is bound by L2 -> SM operand traffic, and a team cannot start its next tile
             // before its appends have drained anyway.)
             const uint32_t wflags = __reduce_or_sync(0xffffffffu, flags);
-            const long long tp2 = FZ_CLOCK();
             if (wflags) {
                 int base = total > 0 ? atomicAdd(&G.st.cnt[q], total) : 0;
                 const size_t off = (size_t)q * G.st.cap;
@@ -292,28 +341,13 @@ filter_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
                     ptx::tmem_ld_32x32(t_row + c * 32, ra);
                     ptx::tmem_ld_wait(ra);
                     if (flags & (1u << c)) {
-                        uint32_t w4[4] = {0, 0, 0, 0};
-                        if constexpr (kCodes) {
-                            // (dynamic index into the register array would spill: select with a chain of compares)
-#pragma unroll
-                            for (int cc = 0; cc < kBN / 32; ++cc)
-                                if (cc == c) { w4[0] = cw[cc].x; w4[1] = cw[cc].y; w4[2] = cw[cc].z; w4[3] = cw[cc].w; }
-                        }
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
-                            float v = __uint_as_float(ra[j]);
-                            bool hit;
-                            if constexpr (kCodes) {
-                                const float x = fmaf(v, gh, code_decode(w4[j >> 3], j & 7));
-                                hit = x > tau && (ra[j] != 0u || ((w4[j >> 3] >> (4 * (j & 7))) & 15u) != 0u);
-                                v = x;
-                            } else {
-                                hit = v > tau;
-                            }
-                            if (hit && c * 32 + j < limit) {
+                            const float v = __uint_as_float(ra[j]);
+                            if (v > tau && c * 32 + j < limit) {
                                 if (base < G.st.cap) {
                                     G.st.score[off + base] = v;
-                                    G.st.id[off + base] = (int32_t)((uint32_t)(d0 + c * 32 + j) | (kCodes ? kPendingBit : 0u));
+                                    G.st.id[off + base] = (int32_t)(d0 + c * 32 + j);
                                 }
                                 ++base;
                             }

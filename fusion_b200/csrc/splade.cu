@@ -67,7 +67,7 @@ constexpr int kRsWarps = 8;
 constexpr int kRsSlots = 512;       // >= 4 x FZ_MAX_QUERY_TERMS
 __global__ void __launch_bounds__(kRsWarps * 32)
 sparse_rescore_kernel(const int32_t* __restrict__ q_ptr, const int32_t* __restrict__ q_term, const float* __restrict__ q_weight,
-                      const int64_t* __restrict__ doc_ptr, const uint2* __restrict__ doc_post, CandState<float> st) {
+                      const int64_t* __restrict__ doc_ptr, const uint2* __restrict__ doc_post, CandState<float> st, int force_all) {
     __shared__ int s_key[kRsSlots];
     __shared__ float s_val[kRsSlots];
     const int q = blockIdx.x;
@@ -89,26 +89,50 @@ sparse_rescore_kernel(const int32_t* __restrict__ q_ptr, const int32_t* __restri
     }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // Software pipeline over this warp's candidates: the id of candidate i + 2 and the posting range of candidate i + 1 are
+    // in flight while candidate i's postings are summed (each step of the chain id -> doc_ptr -> postings is a dependent
+    // global load of ~1 us under load).
+    auto load_id = [&](int i) { return i < n ? st.id[off + i] : 0; };
+    auto is_pending = [&](int32_t id) { return force_all != 0 || id < 0; };
+    int32_t id1 = load_id(warp), id2 = load_id(warp + kRsWarps);
+    long long a1 = 0, b1 = 0;
+    if (warp < n && is_pending(id1)) {
+        const int d = (int)((uint32_t)id1 & ~kPendingBit);
+        a1 = __ldg(doc_ptr + d);
+        b1 = __ldg(doc_ptr + d + 1);
+    }
     for (int i = warp; i < n; i += kRsWarps) {
-        const int32_t id = st.id[off + i];
-        if (id >= 0) continue;                                      // rescored in an earlier round
-        const int doc = (int)((uint32_t)id & ~kPendingBit);
-        const long long p0 = doc_ptr[doc], p1 = doc_ptr[doc + 1];
+        const int32_t id = id1;
+        const long long p0 = a1, p1 = b1;
+        id1 = id2;
+        id2 = load_id(i + 2 * kRsWarps);
+        if (i + kRsWarps < n && is_pending(id1)) {
+            const int d = (int)((uint32_t)id1 & ~kPendingBit);
+            a1 = __ldg(doc_ptr + d);
+            b1 = __ldg(doc_ptr + d + 1);
+        }
+        if (!is_pending(id)) continue;                              // rescored in an earlier round
         float acc = 0.f;
-        for (long long p = p0 + lane; p < p1; p += 32) {
-            const uint2 e = __ldg(doc_post + p);
-            unsigned slot = (e.x * 2654435761u) >> 23;
-            while (true) {
-                const int key = s_key[slot];
-                if (key == (int)e.x) { acc = fmaf(__uint_as_float(e.y), s_val[slot], acc); break; }
-                if (key == -1) break;
-                slot = (slot + 1) & (kRsSlots - 1);
+        for (long long p = p0 + lane; p < p1; p += 128) {           // up to four independent loads in flight per lane
+            uint2 e[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) e[u] = p + 32 * u < p1 ? __ldg(doc_post + p + 32 * u) : make_uint2(0xffffffffu, 0u);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (e[u].x == 0xffffffffu) continue;
+                unsigned slot = (e[u].x * 2654435761u) >> 23;
+                while (true) {
+                    const int key = s_key[slot];
+                    if (key == (int)e[u].x) { acc = fmaf(__uint_as_float(e[u].y), s_val[slot], acc); break; }
+                    if (key == -1) break;
+                    slot = (slot + 1) & (kRsSlots - 1);
+                }
             }
         }
         acc = warp_sum(acc);
         if (lane == 0) {
             st.score[off + i] = acc;
-            st.id[off + i] = doc;
+            st.id[off + i] = (int32_t)((uint32_t)id & ~kPendingBit);
         }
     }
 }
@@ -147,7 +171,8 @@ size_t fz_splade_topk_workspace_bytes(int n_queries, int k, int cap, int head_di
     return splade_fixed_bytes(n_queries, cap, head_dim) + tiles * q_pad * 128;
 }
 
-int fz_splade_topk(const fz_postings_t* tail, const fz_splade_head_t* head, const int32_t* q_ptr, const int32_t* q_term,
+int fz_splade_topk(const fz_postings_t* tail, const fz_splade_head_t* head, const fz_postings_t* boot, const int32_t* q_ptr,
+                   const int32_t* q_term,
                    const float* q_weight, int n_queries, int k, int64_t doc_base, int cap, int growth, float* out_scores,
                    int32_t* out_ids, int32_t* out_status, void* ws, size_t ws_bytes, const fz_shard_sync_t* sync,
                    fz_stream_t stream_) {
@@ -215,16 +240,41 @@ int fz_splade_topk(const fz_postings_t* tail, const fz_splade_head_t* head, cons
     T.qparam = qparam;
     T.codes = codes;
     T.status = out_status;
+    { const char* e = getenv("FZ_DEBUG_TAIL"); T.debug = e ? atoi(e) : 0; }
 
     const bool synced = sync && sync->hook;
     FZ_REQUIRE(!synced || (sync->exchange && sync->n_shards >= 1 && sync->sched_docs >= N), "bad shard sync");
     const long long SN = synced ? (long long)sync->sched_docs : N;     // the schedule every shard follows
-    // the first round takes every doc that shares a term with the query (no threshold yet): it must fit the buffer
-    long long lo = 0, hi = (long long)(cap / 256) * 256;
-    if (hi > 2048 && 2048 >= 2 * k) hi = 2048;
-    if (hi < 256) hi = 256;
-    if (hi > max_round) hi = max_round;
-    FZ_REQUIRE(hi >= 256 && hi <= cap, "cap=%d too small for a first round of 256 docs", cap);
+    auto rescore = [&](int force_all) -> int {
+        ProfScope prof("splade_rescore", stream);
+        sparse_rescore_kernel<<<n_queries, kRsWarps * 32, 0, stream>>>(q_ptr, q_term, q_weight, head->doc_ptr,
+                                                                        (const uint2*)head->doc_post, st, force_all);
+        FZ_LAUNCH_CHECK();
+        return FZ_OK;
+    };
+    long long lo = 0, hi;
+    if (boot) {
+        // threshold bootstrap on the shard's first documents with the general kernel (no rescoring per emitted doc), then
+        // its survivors are rescored exactly so that every score in the buffer - and the threshold - is an exact one
+        FZ_REQUIRE(boot->n_docs >= 256 && boot->n_docs % 256 == 0 && boot->n_docs <= N && boot->n_terms == head->n_terms,
+                   "bootstrap index must cover the first n (multiple of 256) docs of the shard");
+        rc = sparse_bootstrap_f32(boot, q_ptr, q_term, q_weight, n_queries, k, st, (head->flags & FZ_SPLADE_UNIT_ROWS) != 0, stream);
+        if (rc) return rc;
+        rc = rescore(1);
+        if (rc) return rc;
+        rc = cand_select<float>(st, n_queries, k, 0.f, false, doc_base, nullptr, nullptr, nullptr, stream, nullptr);
+        if (rc) return rc;
+        lo = boot->n_docs;
+        hi = lo * growth;
+        if (hi - lo > max_round) hi = lo + max_round;
+    } else {
+        // the first round takes every doc that shares a term with the query (no threshold yet): it must fit the buffer
+        hi = (long long)(cap / 256) * 256;
+        if (hi > 2048 && 2048 >= 2 * k) hi = 2048;
+        if (hi < 256) hi = 256;
+        if (hi > max_round) hi = max_round;
+        FZ_REQUIRE(hi >= 256 && hi <= cap, "cap=%d too small for a first round of 256 docs", cap);
+    }
     if (hi > SN) hi = SN;
     while (true) {
         const long long r_lo = lo < N ? lo : N, r_hi = hi < N ? hi : N;
@@ -244,12 +294,8 @@ int fz_splade_topk(const fz_postings_t* tail, const fz_splade_head_t* head, cons
                 filter_gemm_kernel<true><<<grid, kGemmThreads, kGemmSmem, stream>>>(tmap_q, tmap_d, G);
                 FZ_LAUNCH_CHECK();
             }
-            {
-                ProfScope prof("splade_rescore", stream);
-                sparse_rescore_kernel<<<n_queries, kRsWarps * 32, 0, stream>>>(q_ptr, q_term, q_weight, head->doc_ptr,
-                                                                                (const uint2*)head->doc_post, st);
-                FZ_LAUNCH_CHECK();
-            }
+            rc = rescore(0);
+            if (rc) return rc;
         }
         const bool last = hi >= SN;
         const float* floor = last ? nullptr : shard_floor<float>(sync, st, n_queries, k, 0.f, stream, &rc);

@@ -2,6 +2,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "topk_state.cuh"
 
 namespace fz {
 
@@ -16,9 +17,16 @@ struct TailCodeArgs {
     const float2* qparam;        // [n_queries] (gh, g)
     uint32_t* codes;             // [((r_hi - r_lo + 255) / 256 * 8 + chunk) * q_pad + q] x 4 words of 8 codes
     int32_t* status;             // FZ_STATUS_FALLBACK when a tail sum left the code range
+    int debug;                   // timing experiments only (FZ_DEBUG_TAIL): 1 = no global stores, 2 = no posting walk
 };
 
 // one CTA per (query, group of FZ_COARSE_TILES tail tiles) of the round
 int launch_tail_codes(const TailCodeArgs& A, cudaStream_t stream);
+
+// Threshold bootstrap: the general inverted-index kernel over a small index of the shard's FIRST documents (all terms),
+// geometric rounds + cand_select into an initialised candidate state.  Leaves the k best of those documents (scores of the
+// fixed-point kernel when `fixed_point`: the caller rescores them) and their k-th score as the threshold.
+int sparse_bootstrap_f32(const fz_postings_t* ix, const int32_t* q_ptr, const int32_t* q_term, const float* q_weight,
+                         int n_queries, int k, const CandState<float>& st, bool fixed_point, cudaStream_t stream);
 
 }  // namespace fz

@@ -66,8 +66,8 @@ def build_postings(term_ptr: torch.Tensor, post_doc: torch.Tensor, post_val: tor
     dev = post_doc.device
     n_terms = term_ptr.numel() - 1
     vec = 16 // post_val.element_size()                     # 4 fp32 weights / 2 fp64 impacts per 16-byte load
-    if tile_docs % 4 or not (4 <= tile_docs <= 8192):
-        raise FusionB200Error(f"tile_docs={tile_docs} must be a multiple of 4 in [4, 8192]")
+    if tile_docs % 4 or not (4 <= tile_docs <= 32768):      # (the K2 kernels take <= 8192; the SPLADE tail kernel 32768)
+        raise FusionB200Error(f"tile_docs={tile_docs} must be a multiple of 4 in [4, 32768]")
     n_tiles = (n_docs + tile_docs - 1) // tile_docs
     df = term_ptr[1:] - term_ptr[:-1]
     if tiled_min is None:
@@ -236,7 +236,8 @@ class LexicalIndex:
 
 
 SP_HEAD_DIM = int(os.environ.get("FZ_SPLADE_HEAD", 192))           # head terms scored on the tensor cores (multiple of 64, <= 256)
-SP_TAIL_TILE_DOCS = int(os.environ.get("FZ_TILE_DOCS_TAIL", 8192))   # docs per fixed-point accumulator tile of the tail kernel
+SP_TAIL_TILE_DOCS = int(os.environ.get("FZ_TILE_DOCS_TAIL", 4096))   # docs per fixed-point accumulator tile of the tail kernel
+SP_BOOT_DOCS = int(os.environ.get("FZ_SPLADE_BOOT", 262144))         # docs of the threshold bootstrap (0 = none)
 
 
 class SparseIndex:
@@ -253,7 +254,8 @@ class SparseIndex:
 
     def __init__(self, doc_ptr, doc_term, doc_weight, vocab_size: int, similarity: str = "cos_sim", device="cuda",
                  doc_base: int = 0, tile_docs: int = SP_TILE_DOCS, tiled_min: int | None = None,
-                 dense_frac: float = DENSE_FRAC, head_dim: int | None = None, tail_tile_docs: int | None = None):
+                 dense_frac: float = DENSE_FRAC, head_dim: int | None = None, tail_tile_docs: int | None = None,
+                 boot_docs: int | None = None):
         if similarity not in ("cos_sim", "dot"):
             raise FusionB200Error(f"unknown similarity {similarity!r}")
         self.similarity, self.vocab_size, self.doc_base, self.tile_docs = similarity, int(vocab_size), int(doc_base), int(tile_docs)
@@ -277,6 +279,12 @@ class SparseIndex:
         head_dim = SP_HEAD_DIM if head_dim is None else int(head_dim)
         if self.nonneg and head_dim > 0 and self.n_docs > 0:
             self._build_head_tail(row, term, w, head_dim, int(tail_tile_docs or SP_TAIL_TILE_DOCS))
+            # threshold bootstrap (ops.splade_topk): a general index over the first boot_docs docs, when they are a small part
+            # of the shard.  Sharded runs must pass the same boot_docs on every rank (the round schedule starts there).
+            boot_docs = SP_BOOT_DOCS if boot_docs is None else int(boot_docs)
+            boot_docs = boot_docs // 256 * 256
+            if boot_docs >= 256 and self.n_docs >= 8 * boot_docs:
+                self.head.boot = self._general_view(boot_docs)
 
     def _build_head_tail(self, row, term, w, head_dim, tail_tile_docs):
         dev, n, v = self.device, self.n_docs, self.vocab_size
@@ -297,20 +305,28 @@ class SparseIndex:
         del th, m
         order, term_ptr_t, _ = _term_major_csr(row_t, term_t, n, v)
         tail_tile_docs = max(256, min(tail_tile_docs, (n + 255) // 256 * 256))
+        # (tail tiles are small: terms rarer than one posting per tile stay plain doc-ascending lists with coarse marks)
+        tail_tiled_min = self.tiled_min if self.tiled_min is not None else int(os.environ.get("FZ_TAIL_TILED_MIN", 4096))
         tail = build_postings(term_ptr_t, row_t[order].to(torch.int32), w_t[order].contiguous(), n, tail_tile_docs,
-                              self.tiled_min, dense_frac=0.0)
-        self.head = ops.SpladeHeadView(head, term_head, term_max, self.doc_ptr, self.doc_post, tail, head_dim, v, n)
+                              tail_tiled_min, dense_frac=0.0)
+        self.head = ops.SpladeHeadView(head, term_head, term_max, self.doc_ptr, self.doc_post, tail, head_dim, v, n,
+                                       unit_rows=self.similarity == "cos_sim")
+
+    def _general_view(self, n_docs: int) -> ops.PostingsView:
+        """The three-form inverted index over all terms of the first ``n_docs`` docs."""
+        nnz = int(self.doc_ptr[n_docs])
+        lens = self.doc_ptr[1:n_docs + 1] - self.doc_ptr[:n_docs]
+        row = torch.repeat_interleave(torch.arange(n_docs, device=self.device), lens)
+        term = self.doc_post[:nnz, 0].long()
+        w = self.doc_post[:nnz, 1].contiguous().view(torch.float32)
+        order, term_ptr, _ = _term_major_csr(row, term, n_docs, self.vocab_size)
+        return build_postings(term_ptr, row[order].to(torch.int32), w[order].contiguous(), n_docs, self.tile_docs,
+                              self.tiled_min, self.dense_frac)
 
     def view(self) -> ops.PostingsView:
         """The general inverted index over all terms (built on first use)."""
         if self._view is None:
-            lens = self.doc_ptr[1:] - self.doc_ptr[:-1]
-            row = torch.repeat_interleave(torch.arange(self.n_docs, device=self.device), lens)
-            term = self.doc_post[:, 0].long()
-            w = self.doc_post[:, 1].contiguous().view(torch.float32)
-            order, self.term_ptr, _ = _term_major_csr(row, term, self.n_docs, self.vocab_size)
-            self._view = build_postings(self.term_ptr, row[order].to(torch.int32), w[order].contiguous(), self.n_docs,
-                                        self.tile_docs, self.tiled_min, self.dense_frac)
+            self._view = self._general_view(self.n_docs)
         return self._view
 
     def topk(self, q_ptr, q_term, q_weight, k: int, cap: int = ops.DEFAULT_CAP, sync: "ops.ShardSync | None" = None):
@@ -324,7 +340,7 @@ class SparseIndex:
         if self.head is not None:
             b += self.head.nbytes()
         if self._view is not None:
-            b += self._view.nbytes() + self.term_ptr.numel() * 8
+            b += self._view.nbytes()
         return b
 
 

@@ -396,16 +396,20 @@ class SpladeHeadView:
     head_dim: int
     n_terms: int
     n_docs: int
+    unit_rows: bool = False       # cos_sim index: every doc vector has norm <= 1
+    boot: "PostingsView | None" = None    # general index over the first boot.n_docs docs (threshold bootstrap)
 
     def nbytes(self) -> int:
-        return self.tail.nbytes() + sum(t.numel() * t.element_size() for t in (self.head_bf16, self.term_head, self.term_max))
+        return (self.tail.nbytes() + (self.boot.nbytes() if self.boot is not None else 0) +
+                sum(t.numel() * t.element_size() for t in (self.head_bf16, self.term_head, self.term_max)))
 
     def c_struct(self) -> _lib.SpladeHead:
         return _lib.SpladeHead(self.head_bf16.data_ptr(), self.term_head.data_ptr(), self.term_max.data_ptr(),
-                               self.doc_ptr.data_ptr(), self.doc_post.data_ptr(), self.head_dim, self.n_terms, self.n_docs)
+                               self.doc_ptr.data_ptr(), self.doc_post.data_ptr(), self.head_dim, self.n_terms, self.n_docs,
+                               1 if self.unit_rows else 0, 0)
 
 
-SPLADE_GROWTH = 3               # rounds grow 3x: a round emits the docs whose score UPPER BOUND beats the running k-th score
+SPLADE_GROWTH = 2               # rounds grow 2x: a round emits the docs whose score UPPER BOUND beats the running k-th score
 SPLADE_MAX_ROUND_DOCS = 1 << 21    # bounds the code buffer: n_queries * max_round_docs / 2 bytes
 
 
@@ -436,7 +440,8 @@ def splade_topk(index, q_ptr, q_term, q_weight, k: int, doc_base: int = 0, cap: 
     ws = _ws(lib.fz_splade_topk_workspace_bytes(nq, k_eff, cap, hv.head_dim, round_docs), dev)
     sc = _SyncCall(sync, nq, torch.float32, dev, k)
     tail, head = hv.tail.c_struct(), hv.c_struct()
-    rc = lib.fz_splade_topk(C.byref(tail), C.byref(head), _ptr(q_ptr), _ptr(q_term), _ptr(q_weight), nq, k_eff, doc_base, cap,
+    boot = hv.boot.c_struct() if hv.boot is not None else None
+    rc = lib.fz_splade_topk(C.byref(tail), C.byref(head), C.byref(boot) if boot is not None else None, _ptr(q_ptr), _ptr(q_term), _ptr(q_weight), nq, k_eff, doc_base, cap,
                             growth, _ptr(out_s), _ptr(out_i), _ptr(status), _ptr(ws), ws.numel(), sc.ref(), _stream(out_s))
     sc.reraise()
     check(rc, "fz_splade_topk")

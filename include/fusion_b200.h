@@ -270,6 +270,10 @@ int fz_sparse_scores_f32(const fz_postings_t* index, const int32_t* q_ptr, const
  *   head_bf16 [n_docs, head_dim]: weight of head term j in doc d (bf16, row-major, head_dim % 64 == 0, 64..256)
  *   term_head [n_terms]: head column of a term, -1 for tail terms;  term_max [n_terms]: max weight of the term in the shard
  *   doc_ptr [n_docs + 1], doc_post [nnz] (int32 term, float weight) pairs: the doc-major copy, terms in any order
+ * boot_index (may be NULL): a general inverted index (all terms, any storage forms) over the FIRST boot_index->n_docs docs of
+ * the shard.  Those docs are scored with the K2 kernel first - its exact scores cost no rescoring - so that the head/tail
+ * rounds start with a threshold that few docs beat: a round emits about k docs per doubling of the range whatever its size,
+ * and every emitted doc costs a ~0.75 KB rescoring gather.
  * Queries that leave the fast path's contract get FZ_STATUS_FALLBACK (or FZ_STATUS_OVERFLOW) in out_status and an
  * unspecified row: the caller re-runs those with fz_sparse_topk_f32 on the full index.
  * ---------------------------------------------------------------------------------------------------------- */
@@ -282,11 +286,15 @@ typedef struct fz_splade_head {
     int32_t head_dim;
     int32_t n_terms;
     int64_t n_docs;
+    int32_t flags;                /* FZ_SPLADE_UNIT_ROWS: every doc vector has norm <= 1 (cos_sim index) */
+    int32_t reserved;
 } fz_splade_head_t;
+#define FZ_SPLADE_UNIT_ROWS 1
 
 /* max_round_docs bounds the code buffer (n_queries * max_round_docs / 2 bytes): rounds never span more documents */
 size_t fz_splade_topk_workspace_bytes(int n_queries, int k, int cap, int head_dim, int64_t max_round_docs);
-int fz_splade_topk(const fz_postings_t* tail_index, const fz_splade_head_t* head, const int32_t* q_ptr, const int32_t* q_term,
+int fz_splade_topk(const fz_postings_t* tail_index, const fz_splade_head_t* head, const fz_postings_t* boot_index,
+                   const int32_t* q_ptr, const int32_t* q_term,
                    const float* q_weight, int n_queries, int k, int64_t doc_base, int cap, int growth, float* out_scores,
                    int32_t* out_ids, int32_t* out_status, void* ws, size_t ws_bytes,
                    const fz_shard_sync_t* sync /* may be NULL */, fz_stream_t stream);

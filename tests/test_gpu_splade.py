@@ -37,7 +37,8 @@ def test_splade_pipeline_vs_dense_oracle(head_dim):
     _sets_equal_above_cut(ids.cpu().numpy(), sc.cpu().numpy(), eids.numpy(), esc.numpy(), 1e-5)
 
 
-def test_splade_pipeline_equals_inverted_index_path():
+@pytest.mark.parametrize("boot_docs", [0, 4096])
+def test_splade_pipeline_equals_inverted_index_path(boot_docs):
     """Mid-size corpus, k = 1000, default cap: the fast path returns what the general inverted-index kernel returns
     (exact fp32 scores in both; the summation order differs, hence 1e-6 absolute)."""
     from fusion_b200 import ops
@@ -45,7 +46,8 @@ def test_splade_pipeline_equals_inverted_index_path():
     vocab, n_docs, nq, k = 8000, 120_000, 64, 1000
     dp, dt, dw = synth.splade_vectors(n_docs, vocab, 100, 8, 400, seed=311)
     qp, qt, qw = synth.splade_vectors(nq, vocab, 20, 2, 64, seed=312)
-    ix = SparseIndex(dp, dt, dw, vocab, "cos_sim", head_dim=128)
+    ix = SparseIndex(dp, dt, dw, vocab, "cos_sim", head_dim=128, boot_docs=boot_docs)
+    assert (ix.head.boot is not None) == (boot_docs > 0)
     q_ptr, q_term, q_w = sparse_queries(qp, qt, qw, "cos_sim", ix.device)
     sc, ids = ops.splade_topk(ix, q_ptr, q_term, q_w, k)
     sc2, ids2 = ops.sparse_topk(ix.view(), q_ptr, q_term, q_w, k)
