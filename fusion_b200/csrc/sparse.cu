@@ -557,266 +557,6 @@ static bool splade_fixed_point_enabled() {
 
 template <typename AccT> static int check_index(const fz_postings_t* ix);
 
-// ------------------------------------------------------------------------------------ SPLADE tail codes (splade.cu)
-// The SPLADE pipeline scores the HEAD terms (the ~200 most frequent ones: 95+ % of all (query term, posting) pairs) on the
-// tensor cores (filter_gemm.cuh) and only needs an UPPER BOUND of the remaining tail sum per (query, doc) to decide which
-// docs can still reach the top-k; the survivors are rescored exactly.  This kernel produces that bound: the tail terms'
-// postings are scattered into fixed-point shared-memory accumulators (integer atomics: native, commutative, every addend
-// rounded up), one warp per term and no barrier between terms, and every doc's sum is rounded up into a 4-bit code
-// (filter_gemm.cuh: kCodeBase) written where the GEMM epilogue reads it: 16 bytes per (query, 32-doc chunk).
-constexpr uint32_t kTailCodeBase = 0x3C000000u;   // == kCodeBase (filter_gemm.cuh)
-
-// Every WARP owns one (query, tile) at a time - its own code words, its own copy of the query's resolved terms, no
-// CTA-wide barrier anywhere.  (Three CTA-per-(query, tile) versions of this kernel all spent ~60 % of their warp time in
-// barriers: a tile holds ~10 active terms of ~50-200 postings each, so most warps of a CTA wait for the one that is still
-// behind a posting load.)  The accumulators ARE the 4-bit codes: a posting's contribution is rounded up to a code level,
-// and a doc that is hit again combines the two codes (smallest level >= the sum of the two levels) with a compare-and-swap
-// on the 32-bit word that holds 8 docs' codes.  88 % of the docs are never hit, 94 % of the others exactly once.
-constexpr int kTailWarps = 8;
-
-// smallest code c with decode(c) >= x (x >= B0); > 15 when x is beyond the top level
-__device__ __forceinline__ uint32_t tail_code_of(float x) {
-    return (__float_as_uint(x) - kTailCodeBase + 0x3FFFFFu) >> 22;
-}
-
-struct TailWarpTerms {              // one warp's query, resolved for the CTA's tile group
-    long long base[kMaxTerms];
-    int aux[kMaxTerms];
-    int kind[kMaxTerms];
-    float w[kMaxTerms];             // query weight * gain
-};
-
-__global__ void __launch_bounds__(kTailWarps * 32) tail_codes_kernel(const TailCodeArgs T, const SparseArgs<float> A) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int tile_docs = A.ix.tile_docs;
-    const int cs_words = tile_docs / 8 + 4;                                  // + the dump word of the padding postings
-    uint32_t* cs = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)warp * cs_words;
-    TailWarpTerms& S = reinterpret_cast<TailWarpTerms*>(smem_raw + (size_t)kTailWarps * cs_words * 4)[warp];
-    const float* __restrict__ short_val = reinterpret_cast<const float*>(A.ix.post_val);
-    const float* __restrict__ tiled_val = reinterpret_cast<const float*>(A.ix.tiled_val);
-
-    const int n_qb = (A.n_queries + kTailWarps - 1) / kTailWarps;
-    const int group = A.group_lo + blockIdx.x / n_qb;
-    const int q = (blockIdx.x % n_qb) * kTailWarps + warp;
-    if (q >= A.n_queries) return;                                            // (no CTA-wide barrier below)
-    const int t_begin = max(group * kGroupTiles, A.tile_lo), t_end = min((group + 1) * kGroupTiles, A.tile_hi);
-    const float gain = T.qparam[q].y;
-    const long long r_hi_pad = (T.r_hi + 255) / 256 * 256;
-    uint4* __restrict__ out4 = reinterpret_cast<uint4*>(T.codes) + q;       // [(doc - r_lo) / 32][q_pad] x 16 bytes
-
-    // ---- resolve the query's terms for this tile group (lane i holds terms i, i + 32, ...)
-    const int qb = A.q_ptr[q];
-    const int nt = min(A.q_ptr[q + 1] - qb, kMaxTerms);
-    const int n_chunks = (nt + 31) >> 5;
-    for (int i = lane; i < n_chunks * 32; i += 32) {
-        int kind = kKindNone, aux = 0;
-        long long base = 0;
-        float w = 0.f;
-        if (i < nt) {
-            const int term = A.q_term[qb + i];
-            w = (A.q_weight ? A.q_weight[qb + i] : 1.0f) * gain;
-            if (term >= 0 && term < A.ix.n_terms) {
-                const int slot = A.ix.term_slot[term];
-                if (slot >= 0) {
-                    kind = kKindTiled;
-                    base = A.ix.tiled_base[slot];
-                    aux = slot;
-                } else if (slot == -1) {
-                    const long long b0 = A.ix.term_ptr[term];
-                    if (A.ix.term_ptr[term + 1] > b0) {
-                        const uint16_t* cm = A.ix.short_coarse + (size_t)term * (A.ix.n_coarse + 1) + group;
-                        const int c0 = cm[0], c1 = cm[1];
-                        if (c1 > c0) {
-                            kind = kKindShort;
-                            base = b0 + c0;
-                            aux = c1 - c0;
-                        }
-                    }
-                }
-            }
-        }
-        S.base[i] = base;
-        S.aux[i] = aux;
-        S.kind[i] = kind;
-        S.w[i] = w;
-    }
-    for (int i = lane * 4; i < cs_words; i += 128) *reinterpret_cast<uint4*>(cs + i) = make_uint4(0, 0, 0, 0);
-    __syncwarp();
-
-    bool bad = false;
-    // one posting: value * (query weight * gain), rounded up to a code, into doc slot o of the tile
-    auto hit = [&](unsigned o, float v, float jw) {
-        const uint32_t c = tail_code_of(__fadd_ru(__fmul_ru(v, jw), 0.0078125f));
-        if (c == 0u) return;                    // padding posting (value 0)
-        if (c > 15u) bad = true;
-        uint32_t* w = cs + (o >> 3);
-        const int sh = 4 * (o & 7);
-        uint32_t old = *w;
-        while (true) {
-            const uint32_t nib = (old >> sh) & 15u;
-            uint32_t nc = c;
-            if (nib != 0u) {                    // second hit of this doc: level(nib) + level(c), rounded up again
-                const float a = __fsub_ru(__uint_as_float(kTailCodeBase | (nib << 22)), 0.0078125f);
-                nc = tail_code_of(__fadd_ru(a, __uint_as_float(kTailCodeBase | (min(c, 15u) << 22))));
-                if (nc > 15u) bad = true;
-            }
-            nc = min(nc, 15u);
-            const uint32_t seen = atomicCAS(w, old, (old & ~(15u << sh)) | (nc << sh));
-            if (seen == old) break;
-            old = seen;
-        }
-    };
-    auto off_of = [&](int c, int tile) -> uint32_t {       // segment start of this lane's term of chunk c in `tile`
-        const int i = c * 32 + lane;
-        if (i < nt && S.kind[i] == kKindTiled && tile <= A.ix.n_tiles)
-            return __ldg(A.ix.tiled_tile_off + (size_t)S.aux[i] * (A.ix.n_tiles + 1) + tile);
-        return 0;
-    };
-    uint32_t oc[kMaxTerms / 32], on[kMaxTerms / 32];       // this tile's and the next tile's segment starts
-#pragma unroll
-    for (int c = 0; c < kMaxTerms / 32; ++c) {
-        oc[c] = c < n_chunks ? off_of(c, t_begin) : 0;
-        on[c] = c < n_chunks ? off_of(c, t_begin + 1) : 0;
-    }
-
-    for (int tile = t_begin; tile < t_end; ++tile) {
-        const long long d_lo = (long long)tile * tile_docs;
-        const int dl = (int)d_lo;
-#pragma unroll
-        for (int c = 0; c < kMaxTerms / 32; ++c) {
-            if (c >= n_chunks) break;
-            const int i = c * 32 + lane;
-            const int kind = S.kind[i];
-            long long lo = S.base[i];
-            int len = 0;
-            if (kind == kKindTiled) {
-                lo += oc[c];
-                len = (int)(on[c] - oc[c]);
-            } else if (kind == kKindShort) {
-                len = S.aux[i];
-            }
-            const float jw = S.w[i];
-            oc[c] = on[c];
-            on[c] = tile + 1 < t_end ? off_of(c, tile + 2) : 0;             // in flight while this tile's postings are walked
-            unsigned m = __ballot_sync(0xffffffffu, len > 0);
-            while (m) {
-                // two terms per step: both terms' first posting loads are in flight before either is consumed
-                const int l0 = __ffs(m) - 1;
-                m &= m - 1;
-                const int l1 = m ? __ffs(m) - 1 : l0;
-                const bool two = l1 != l0;
-                if (two) m &= m - 1;
-                long long lo_[2];
-                int len_[2], kind_[2];
-                float w_[2];
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    const int src = u ? l1 : l0;
-                    lo_[u] = __shfl_sync(0xffffffffu, lo, src);
-                    len_[u] = __shfl_sync(0xffffffffu, len, src);
-                    kind_[u] = __shfl_sync(0xffffffffu, kind, src);
-                    w_[u] = __shfl_sync(0xffffffffu, jw, src);
-                }
-                if (!two) len_[1] = 0;
-                uint2 o_[2];
-                float4 v_[2];
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    o_[u] = make_uint2(0, 0);
-                    v_[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (kind_[u] == kKindTiled) {
-                        if (4 * lane < len_[u]) {
-                            o_[u] = __ldg(reinterpret_cast<const uint2*>(A.ix.tiled_off + lo_[u] + 4 * lane));
-                            v_[u] = __ldg(reinterpret_cast<const float4*>(tiled_val + lo_[u] + 4 * lane));
-                        }
-                    } else if (lane < len_[u]) {
-                        o_[u].x = (unsigned)(__ldg(A.ix.post_doc + lo_[u] + lane) - dl);
-                        v_[u].x = __ldg(short_val + lo_[u] + lane);
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    if (kind_[u] == kKindTiled) {
-                        if (4 * lane < len_[u]) {
-                            hit(o_[u].x & 0xffffu, v_[u].x, w_[u]);        // (padding: offset tile_docs = the dump word, value 0)
-                            hit(o_[u].x >> 16, v_[u].y, w_[u]);
-                            hit(o_[u].y & 0xffffu, v_[u].z, w_[u]);
-                            hit(o_[u].y >> 16, v_[u].w, w_[u]);
-                        }
-                        for (int p = 4 * lane + 128; p < len_[u]; p += 128) {           // long segments: the rest, plainly
-                            const uint2 o = __ldg(reinterpret_cast<const uint2*>(A.ix.tiled_off + lo_[u] + p));
-                            const float4 v = __ldg(reinterpret_cast<const float4*>(tiled_val + lo_[u] + p));
-                            hit(o.x & 0xffffu, v.x, w_[u]);
-                            hit(o.x >> 16, v.y, w_[u]);
-                            hit(o.y & 0xffffu, v.z, w_[u]);
-                            hit(o.y >> 16, v.w, w_[u]);
-                        }
-                    } else {
-                        if (lane < len_[u] && o_[u].x < (unsigned)tile_docs) hit(o_[u].x, v_[u].x, w_[u]);
-                        for (int p = lane + 32; p < len_[u]; p += 32) {
-                            const unsigned o = (unsigned)(__ldg(A.ix.post_doc + lo_[u] + p) - dl);
-                            if (o < (unsigned)tile_docs) hit(o, __ldg(short_val + lo_[u] + p), w_[u]);
-                        }
-                    }
-                }
-            }
-        }
-        __syncwarp();           // every posting of the tile has landed
-
-        // ---- the tile's code words -> the layout the GEMM epilogue reads: 16 bytes per (32-doc chunk, query); a lane zeroes
-        // what it has copied
-        {
-            const long long c_lo = max(d_lo, T.r_lo), c_hi = min(d_lo + tile_docs, r_hi_pad);      // multiples of 256
-            const int i_lo = (int)((c_lo - d_lo) >> 5), i_hi = (int)((c_hi - d_lo) >> 5);
-            // (may point below the buffer when the round starts inside the tile: only [i_lo, i_hi) is touched)
-            uint4* __restrict__ dst = out4 + ((d_lo - T.r_lo) >> 5) * (long long)T.q_pad;
-            for (int i = lane; i < tile_docs / 32; i += 32) {
-                uint4* src = reinterpret_cast<uint4*>(cs) + i;
-                if (i >= i_lo && i < i_hi && T.debug != 1) dst[(long long)i * T.q_pad] = *src;
-                *src = make_uint4(0, 0, 0, 0);
-            }
-        }
-        __syncwarp();
-    }
-    if (bad) atomicOr(&T.status[q], FZ_STATUS_FALLBACK);
-}
-
-int launch_tail_codes(const TailCodeArgs& T, cudaStream_t stream) {
-    const fz_postings_t* ix = &T.ix;
-    FZ_REQUIRE(ix->term_ptr && ix->term_slot && ix->short_coarse, "null index pointer");
-    FZ_REQUIRE(ix->n_tiled == 0 || (ix->tiled_base && ix->tiled_tile_off && ix->tiled_off && ix->tiled_val), "tiled postings missing");
-    FZ_REQUIRE(ix->tile_docs >= 256 && ix->tile_docs <= 16384 && ix->tile_docs % 256 == 0 && ix->n_dense == 0,
-               "tail index: tile_docs must be a multiple of 256 in [256, 16384], no dense rows");
-    FZ_REQUIRE(ix->n_docs >= 1 && ix->n_docs < (1ll << 31), "n_docs out of range");
-    FZ_REQUIRE(ix->n_tiles == (int)ceil_div<long long>(ix->n_docs, ix->tile_docs), "n_tiles inconsistent with n_docs");
-    FZ_REQUIRE(ix->n_coarse == (ix->n_tiles + FZ_COARSE_TILES - 1) / FZ_COARSE_TILES, "n_coarse inconsistent with n_tiles");
-    FZ_REQUIRE(T.r_lo % 256 == 0 && T.r_hi > T.r_lo, "tail round must start on a multiple of 256");
-    const size_t smem = (size_t)kTailWarps * ((size_t)(ix->tile_docs / 8 + 4) * 4 + sizeof(TailWarpTerms));
-    static bool attr = false;
-    if (!attr) {
-        FZ_CUDA(cudaFuncSetAttribute(tail_codes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        attr = true;
-    }
-    SparseArgs<float> A;
-    memset(&A, 0, sizeof(A));
-    A.ix = *ix;
-    A.q_ptr = T.q_ptr;
-    A.q_term = T.q_term;
-    A.q_weight = T.q_weight;
-    A.n_queries = T.n_queries;
-    A.tile_lo = (int)(T.r_lo / ix->tile_docs);
-    A.tile_hi = (int)ceil_div<long long>(T.r_hi < ix->n_docs ? T.r_hi : ix->n_docs, ix->tile_docs);
-    if (A.tile_hi <= A.tile_lo) A.tile_hi = A.tile_lo + 1;
-    A.group_lo = A.tile_lo / kGroupTiles;
-    const long long blocks = (long long)(ceil_div(A.tile_hi, kGroupTiles) - A.group_lo) * ceil_div(T.n_queries, kTailWarps);
-    FZ_REQUIRE(blocks < (1ll << 31), "grid too large");
-    ProfScope prof("splade_tail_codes", stream);
-    tail_codes_kernel<<<(unsigned)blocks, kTailWarps * 32, smem, stream>>>(T, A);
-    FZ_LAUNCH_CHECK();
-    return FZ_OK;
-}
-
 // Queries with fewer than k positive-score docs: append zero-score docs in ascending doc-id order
 // (the reference ranks every document; unmatched ones score exactly 0.0 and tie by index, bm25.py:103-105).
 template <typename AccT>
