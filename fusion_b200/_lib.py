@@ -34,8 +34,8 @@ class Postings(C.Structure):
 class SpladeHead(C.Structure):
     """mirror of fz_splade_head_t"""
     _fields_ = [("head_bf16", C.c_void_p), ("term_head", C.c_void_p), ("term_max", C.c_void_p), ("doc_ptr", C.c_void_p),
-                ("doc_post", C.c_void_p), ("tail_base", C.c_void_p), ("tail_dir", C.c_void_p), ("tail_post", C.c_void_p), ("head_dim", C.c_int32), ("n_terms", C.c_int32), ("n_docs", C.c_int64),
-                ("flags", C.c_int32), ("tail_tile", C.c_int32)]
+                ("doc_post", C.c_void_p), ("head_dim", C.c_int32), ("n_terms", C.c_int32), ("n_docs", C.c_int64),
+                ("flags", C.c_int32), ("reserved", C.c_int32)]
 
 
 SHARD_HOOK = C.CFUNCTYPE(C.c_int, C.c_void_p)      # fz_shard_hook_t
@@ -80,7 +80,7 @@ SIGNATURES = {
     "fz_sparse_scores_f64": (_i, [_p, _p, _p, _i, _p, _p]),
     "fz_sparse_scores_f32": (_i, [_p, _p, _p, _p, _i, _p, _p]),
     "fz_splade_topk_workspace_bytes": (_sz, [_i, _i, _i, _i, _i64]),
-    "fz_splade_topk": (_i, [_p, _p, _p, _p, _p, _i, _i, _i64, _i, _i, _p, _p, _p, _p, _sz, _p, _p]),
+    "fz_splade_topk": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i64, _i, _i, _p, _p, _p, _p, _sz, _p, _p]),
     "fz_dense_topk_workspace_bytes": (_sz, [_i, _i, _i]),
     "fz_dense_topk": (_i, [_p, _p, _p, _p, _i, _i64, _i, _i, _f, _i64, _i, _i, _p, _p, _p, _p, _sz, _p]),
     "fz_dense_topk_filter": (_i, [_p, _p, _i, _i64, _i, _i, _f, _i64, _i, _i, _i, _p, _p, _p, _sz, _p, _p]),

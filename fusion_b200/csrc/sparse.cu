@@ -557,6 +557,210 @@ static bool splade_fixed_point_enabled() {
 
 template <typename AccT> static int check_index(const fz_postings_t* ix);
 
+// ------------------------------------------------------------------------------------ SPLADE tail codes (splade.cu)
+// The SPLADE pipeline scores the HEAD terms (the ~200 most frequent ones: 95+ % of all (query term, posting) pairs) on the
+// tensor cores (filter_gemm.cuh) and only needs an UPPER BOUND of the remaining tail sum per (query, doc) to decide which
+// docs can still reach the top-k; the survivors are rescored exactly.  This kernel produces that bound: the tail terms'
+// postings are scattered into fixed-point shared-memory accumulators (integer atomics: native, commutative, every addend
+// rounded up), one warp per term and no barrier between terms, and every doc's sum is rounded up into a 4-bit code
+// (filter_gemm.cuh: kCodeBase) written where the GEMM epilogue reads it: 16 bytes per (query, 32-doc chunk).
+constexpr uint32_t kTailCodeBase = 0x3C000000u;   // == kCodeBase (filter_gemm.cuh)
+
+constexpr float kTailScale = 67108864.0f;         // 2^26 fixed point of (tail * g) <= kCodeTop
+
+// Round up a fixed-point tail sum into its 4-bit code: smallest c with decode(c) - B0 >= f * 2^-26 (filter_gemm.cuh).
+__device__ __forceinline__ uint32_t tail_code(int f, bool& bad) {
+    const float tv = __fadd_ru(__int2float_ru(f) * (1.0f / kTailScale), 0.0078125f);
+    uint32_t code = (__float_as_uint(tv) - kTailCodeBase + 0x3FFFFFu) >> 22;
+    if (code > 15u || f < 0) { bad = true; code = 15u; }
+    return code;
+}
+
+// The tail terms' postings are scattered into fixed-point shared-memory accumulators (integer atomics: native, commutative,
+// every addend rounded up), one warp per term and no barrier between terms.
+// 256 threads whatever the tile size: per tile a warp's fixed work (loop set-up, barriers) weighs more than the postings
+// it moves, so fewer warps and larger tiles (up to 32768 docs) are what makes this kernel cheap.  The accumulators are
+// zeroed once per CTA: the encode pass takes every touched doc's sum with atomicExch(.., 0) (a doc hit by several terms is
+// encoded by the first reader, the others see 0 and add nothing), which leaves them zero for the next tile.
+constexpr int kTailThreads = 256;
+__global__ void __launch_bounds__(kTailThreads) tail_codes_kernel(const TailCodeArgs T, const SparseArgs<float> A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int* fx = reinterpret_cast<int*>(smem_raw);         // [tile_docs + 4], slot tile_docs = dump of the padding postings
+    uint32_t* cs = reinterpret_cast<uint32_t*>(fx + A.ix.tile_docs + 4);     // [tile_docs / 8] the tile's codes, 8 per word
+    __shared__ TermStatic S;
+    __shared__ TermListFx L[2];
+    const float* __restrict__ short_val = reinterpret_cast<const float*>(A.ix.post_val);
+    const float* __restrict__ tiled_val = reinterpret_cast<const float*>(A.ix.tiled_val);
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    constexpr int n_warps = kTailThreads / 32;
+    const int tile_docs = A.ix.tile_docs;
+
+    const int group = A.group_lo + blockIdx.x / A.n_queries;
+    const int q = blockIdx.x % A.n_queries;
+    const int t_begin = max(group * kGroupTiles, A.tile_lo), t_end = min((group + 1) * kGroupTiles, A.tile_hi);
+    resolve_terms<float>(A, q, group, S);
+    for (int i = t * 4; i < tile_docs + 4; i += kTailThreads * 4) *reinterpret_cast<int4*>(fx + i) = make_int4(0, 0, 0, 0);
+    for (int i = t * 4; i < tile_docs / 8; i += kTailThreads * 4) *reinterpret_cast<uint4*>(cs + i) = make_uint4(0, 0, 0, 0);
+    const float gain = T.qparam[q].y * kTailScale;
+    const long long r_hi_pad = (T.r_hi + 255) / 256 * 256;
+    uint4* __restrict__ out4 = reinterpret_cast<uint4*>(T.codes) + q;       // [(doc - r_lo) / 32][q_pad] x 16 bytes
+    __syncthreads();
+    const int n_tw = S.n <= 32 ? 1 : (S.n + 31) >> 5;
+    uint32_t o0 = tile_offset<float>(A, S, t_begin), o1 = tile_offset<float>(A, S, t_begin + 1);
+    bool bad = false;
+    for (int tile = t_begin; tile < t_end; ++tile) {
+        TermListFx& Lt = L[tile & 1];
+        const long long d_lo = (long long)tile * tile_docs;
+        if (warp < n_tw) {      // the warps that hold the query's terms build the tile's list of active terms
+            const uint32_t o2 = tile + 1 < t_end ? tile_offset<float>(A, S, tile + 2) : 0;
+            long long lo = 0;
+            int len = 0;
+            const int kind = S.kind[t];
+            if (kind == kKindTiled) {
+                lo = S.base[t] + o0;
+                len = (int)(o1 - o0);
+            } else if (kind == kKindShort) {
+                lo = S.base[t];
+                len = S.aux[t];
+            }
+            o0 = o1;
+            o1 = o2;
+            const unsigned bs = __ballot_sync(0xffffffffu, len > 0);
+            int before = __popc(bs & ((1u << lane) - 1));
+            if (n_tw > 1) {
+                // (n_tw <= 4: a named barrier among the term-holding warps only)
+                if (lane == 0) Lt.ballot[warp][1] = bs;
+                asm volatile("bar.sync 1, %0;" ::"r"(32 * n_tw) : "memory");
+                int n_act = 0;
+                for (int w2 = 0; w2 < n_tw; ++w2) {
+                    const int ns = __popc(Lt.ballot[w2][1]);
+                    if (w2 < warp) before += ns;
+                    n_act += ns;
+                }
+                if (t == 0) Lt.n = n_act;
+            } else if (t == 0) {
+                Lt.n = __popc(bs);
+            }
+            if (len > 0) {
+                Lt.lo[before] = lo;
+                Lt.lenkind[before] = len | (kind << 24);
+                Lt.w[before] = S.w[t] * gain;
+            }
+        }
+        __syncthreads();        // list visible (accumulators are zero: set-up / the previous tile's encode pass)
+
+        // ---- scatter: warp w takes terms w, w + 8, ...; integer atomics, no barrier between terms
+        const int n_active = Lt.n;
+        const int dl = (int)d_lo;
+        for (int j = warp; j < n_active; j += n_warps) {
+            const int jlk = Lt.lenkind[j];
+            const int jlen = jlk & 0xffffff;
+            const float jw = Lt.w[j];
+            const long long jlo = Lt.lo[j];
+            if ((jlk >> 24) == kKindTiled) {
+                const uint16_t* __restrict__ op = A.ix.tiled_off + jlo;
+                const float* __restrict__ vp = tiled_val + jlo;
+                for (int i = 4 * lane; i < jlen; i += 128) {
+                    const uint2 o = __ldg(reinterpret_cast<const uint2*>(op + i));
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(vp + i));
+                    atomicAdd(&fx[o.x & 0xffffu], __float2int_ru(v.x * jw));
+                    atomicAdd(&fx[o.x >> 16], __float2int_ru(v.y * jw));
+                    atomicAdd(&fx[o.y & 0xffffu], __float2int_ru(v.z * jw));
+                    atomicAdd(&fx[o.y >> 16], __float2int_ru(v.w * jw));
+                }
+            } else {
+                const int32_t* __restrict__ dj = A.ix.post_doc + jlo;
+                const float* __restrict__ vj = short_val + jlo;
+                for (int p = lane; p < jlen; p += 32) {
+                    const unsigned o = (unsigned)(__ldg(dj + p) - dl);
+                    if (o < (unsigned)tile_docs) atomicAdd(&fx[o], __float2int_ru(__ldg(vj + p) * jw));
+                }
+            }
+        }
+        __syncthreads();        // every term's adds have landed
+
+        // ---- encode only the docs a posting touched (~10 % of the tile): walk the postings again (their offsets come
+        // from L1 now), take each touched doc's sum (leaving 0), round it up into its code, OR it into the code words
+        for (int j = warp; j < n_active; j += n_warps) {
+            const int jlk = Lt.lenkind[j];
+            const int jlen = jlk & 0xffffff;
+            const long long jlo = Lt.lo[j];
+            if ((jlk >> 24) == kKindTiled) {
+                const uint16_t* __restrict__ op = A.ix.tiled_off + jlo;
+                for (int i = 4 * lane; i < jlen; i += 128) {
+                    const uint2 o = __ldg(reinterpret_cast<const uint2*>(op + i));
+                    const unsigned oo[4] = {o.x & 0xffffu, o.x >> 16, o.y & 0xffffu, o.y >> 16};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (oo[u] >= (unsigned)tile_docs) continue;
+                        const int f = atomicExch(&fx[oo[u]], 0);
+                        if (f != 0) atomicOr(&cs[oo[u] >> 3], tail_code(f, bad) << (4 * (oo[u] & 7)));
+                    }
+                }
+            } else {
+                const int32_t* __restrict__ dj = A.ix.post_doc + jlo;
+                for (int p = lane; p < jlen; p += 32) {
+                    const unsigned o = (unsigned)(__ldg(dj + p) - dl);
+                    if (o >= (unsigned)tile_docs) continue;
+                    const int f = atomicExch(&fx[o], 0);
+                    if (f != 0) atomicOr(&cs[o >> 3], tail_code(f, bad) << (4 * (o & 7)));
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- the tile's code words -> the layout the GEMM epilogue reads: 16 bytes per (32-doc chunk, query); the words
+        // are zeroed again by the thread that copied them
+        {
+            const long long c_lo = max(d_lo, T.r_lo), c_hi = min(d_lo + tile_docs, r_hi_pad);      // multiples of 256
+            const int i_lo = (int)((c_lo - d_lo) >> 5), i_hi = (int)((c_hi - d_lo) >> 5);
+            // (may point below the buffer when the round starts inside the tile: only [i_lo, i_hi) is touched)
+            uint4* __restrict__ dst = out4 + ((d_lo - T.r_lo) >> 5) * (long long)T.q_pad;
+            for (int i = i_lo + t; i < i_hi; i += kTailThreads) {
+                uint4* src = reinterpret_cast<uint4*>(cs) + i;
+                dst[(long long)i * T.q_pad] = *src;
+                *src = make_uint4(0, 0, 0, 0);
+            }
+        }
+    }
+    if (bad) atomicOr(&T.status[q], FZ_STATUS_FALLBACK);
+}
+
+int launch_tail_codes(const TailCodeArgs& T, cudaStream_t stream) {
+    const fz_postings_t* ix = &T.ix;
+    FZ_REQUIRE(ix->term_ptr && ix->term_slot && ix->short_coarse, "null index pointer");
+    FZ_REQUIRE(ix->n_tiled == 0 || (ix->tiled_base && ix->tiled_tile_off && ix->tiled_off && ix->tiled_val), "tiled postings missing");
+    FZ_REQUIRE(ix->tile_docs >= 256 && ix->tile_docs <= 32768 && ix->tile_docs % 256 == 0 && ix->n_dense == 0,
+               "tail index: tile_docs must be a multiple of 256 in [256, 32768], no dense rows");
+    FZ_REQUIRE(ix->n_docs >= 1 && ix->n_docs < (1ll << 31), "n_docs out of range");
+    FZ_REQUIRE(ix->n_tiles == (int)ceil_div<long long>(ix->n_docs, ix->tile_docs), "n_tiles inconsistent with n_docs");
+    FZ_REQUIRE(ix->n_coarse == (ix->n_tiles + FZ_COARSE_TILES - 1) / FZ_COARSE_TILES, "n_coarse inconsistent with n_tiles");
+    FZ_REQUIRE(T.r_lo % 256 == 0 && T.r_hi > T.r_lo, "tail round must start on a multiple of 256");
+    const size_t smem = ((size_t)ix->tile_docs + 4) * sizeof(int) + (size_t)ix->tile_docs / 2;
+    static bool attr = false;
+    if (!attr) {
+        FZ_CUDA(cudaFuncSetAttribute(tail_codes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        attr = true;
+    }
+    SparseArgs<float> A;
+    memset(&A, 0, sizeof(A));
+    A.ix = *ix;
+    A.q_ptr = T.q_ptr;
+    A.q_term = T.q_term;
+    A.q_weight = T.q_weight;
+    A.n_queries = T.n_queries;
+    A.tile_lo = (int)(T.r_lo / ix->tile_docs);
+    A.tile_hi = (int)ceil_div<long long>(T.r_hi < ix->n_docs ? T.r_hi : ix->n_docs, ix->tile_docs);
+    if (A.tile_hi <= A.tile_lo) A.tile_hi = A.tile_lo + 1;
+    A.group_lo = A.tile_lo / kGroupTiles;
+    const long long blocks = (long long)(ceil_div(A.tile_hi, kGroupTiles) - A.group_lo) * T.n_queries;
+    FZ_REQUIRE(blocks < (1ll << 31), "grid too large");
+    ProfScope prof("splade_tail_codes", stream);
+    tail_codes_kernel<<<(unsigned)blocks, kTailThreads, smem, stream>>>(T, A);
+    FZ_LAUNCH_CHECK();
+    return FZ_OK;
+}
+
 // Queries with fewer than k positive-score docs: append zero-score docs in ascending doc-id order
 // (the reference ranks every document; unmatched ones score exactly 0.0 and tie by index, bm25.py:103-105).
 template <typename AccT>

@@ -235,8 +235,8 @@ class LexicalIndex:
                                          (self.term_ptr, self.post_doc, self.post_tf, self.doc_len))
 
 
-SP_HEAD_DIM = int(os.environ.get("FZ_SPLADE_HEAD", 192))           # head terms scored on the tensor cores (multiple of 64, <= 256)
-SP_TAIL_TILE = int(os.environ.get("FZ_SPLADE_TAIL_TILE", 512))       # docs per tail tile (x 128 queries x 4 bits of shared memory)
+SP_HEAD_DIM = int(os.environ.get("FZ_SPLADE_HEAD", 256))           # head terms scored on the tensor cores (multiple of 64, <= 256)
+SP_TAIL_TILE_DOCS = int(os.environ.get("FZ_TILE_DOCS_TAIL", 8192))   # docs per fixed-point accumulator tile of the tail kernel
 SP_BOOT_DOCS = int(os.environ.get("FZ_SPLADE_BOOT", 262144))         # docs of the threshold bootstrap (0 = none)
 
 
@@ -254,7 +254,7 @@ class SparseIndex:
 
     def __init__(self, doc_ptr, doc_term, doc_weight, vocab_size: int, similarity: str = "cos_sim", device="cuda",
                  doc_base: int = 0, tile_docs: int = SP_TILE_DOCS, tiled_min: int | None = None,
-                 dense_frac: float = DENSE_FRAC, head_dim: int | None = None,
+                 dense_frac: float = DENSE_FRAC, head_dim: int | None = None, tail_tile_docs: int | None = None,
                  boot_docs: int | None = None):
         if similarity not in ("cos_sim", "dot"):
             raise FusionB200Error(f"unknown similarity {similarity!r}")
@@ -278,7 +278,7 @@ class SparseIndex:
         self.head = None
         head_dim = SP_HEAD_DIM if head_dim is None else int(head_dim)
         if self.nonneg and head_dim > 0 and self.n_docs > 0:
-            self._build_head_tail(row, term, w, head_dim)
+            self._build_head_tail(row, term, w, head_dim, int(tail_tile_docs or SP_TAIL_TILE_DOCS))
             # threshold bootstrap (ops.splade_topk): a general index over the first boot_docs docs, when they are a small part
             # of the shard.  Sharded runs must pass the same boot_docs on every rank (the round schedule starts there).
             boot_docs = SP_BOOT_DOCS if boot_docs is None else int(boot_docs)
@@ -286,7 +286,7 @@ class SparseIndex:
             if boot_docs >= 256 and self.n_docs >= 8 * boot_docs:
                 self.head.boot = self._general_view(boot_docs)
 
-    def _build_head_tail(self, row, term, w, head_dim):
+    def _build_head_tail(self, row, term, w, head_dim, tail_tile_docs):
         dev, n, v = self.device, self.n_docs, self.vocab_size
         if head_dim % 64 or not (64 <= head_dim <= 256):
             raise FusionB200Error(f"head_dim={head_dim} must be 64, 128, 192 or 256")
@@ -300,27 +300,16 @@ class SparseIndex:
         m = th >= 0
         head = torch.zeros((n, head_dim), dtype=torch.bfloat16, device=dev)
         head[row[m].long(), th[m].long()] = w[m].to(torch.bfloat16)
-        # TAIL postings, tile-major (tiles of tail_tile docs), term-sorted inside a tile, + the [tile][term] directory
         m = ~m
-        if v >= (1 << 24):
-            raise FusionB200Error("the SPLADE head/tail pipeline packs term ids into 24 bits")
-        tt = SP_TAIL_TILE
-        n_tt = (n + tt - 1) // tt
-        key = (row[m].long() // tt) * v + term[m].long()                  # (tile, term); stable sort keeps doc order
-        order = torch.sort(key, stable=True).indices
-        cnt = torch.bincount(key, minlength=n_tt * v).view(n_tt, v)
-        del key
-        per_tile = cnt.sum(1)
-        tail_base = torch.zeros(n_tt + 1, dtype=torch.int64, device=dev)
-        tail_base[1:] = torch.cumsum(per_tile, 0)
-        if int(per_tile.max()) >= (1 << 31):
-            raise FusionB200Error("a tail tile holds more than 2^31 postings")
-        tail_dir = torch.zeros((n_tt, v + 1), dtype=torch.int32, device=dev)
-        tail_dir[:, 1:] = torch.cumsum(cnt, 1).to(torch.int32)
-        del cnt
-        tail_post = torch.stack([(row[m] % tt)[order], w[m].view(torch.int32)[order]], dim=1).contiguous()
-        del th, m, order
-        self.head = ops.SpladeHeadView(head, term_head, term_max, self.doc_ptr, self.doc_post, tail_base, tail_dir, tail_post, tt, head_dim, v, n,
+        row_t, term_t, w_t = row[m], term[m], w[m]
+        del th, m
+        order, term_ptr_t, _ = _term_major_csr(row_t, term_t, n, v)
+        tail_tile_docs = max(256, min(tail_tile_docs, (n + 255) // 256 * 256))
+        # (tail tiles are small: terms rarer than one posting per tile stay plain doc-ascending lists with coarse marks)
+        tail_tiled_min = self.tiled_min if self.tiled_min is not None else int(os.environ.get("FZ_TAIL_TILED_MIN", 512))
+        tail = build_postings(term_ptr_t, row_t[order].to(torch.int32), w_t[order].contiguous(), n, tail_tile_docs,
+                              tail_tiled_min, dense_frac=0.0)
+        self.head = ops.SpladeHeadView(head, term_head, term_max, self.doc_ptr, self.doc_post, tail, head_dim, v, n,
                                        unit_rows=self.similarity == "cos_sim")
 
     def _general_view(self, n_docs: int) -> ops.PostingsView:

@@ -392,10 +392,7 @@ class SpladeHeadView:
     term_max: torch.Tensor        # float32 [V]
     doc_ptr: torch.Tensor         # int64 [N+1]
     doc_post: torch.Tensor        # int32 [nnz, 2]: (term, weight bits)
-    tail_base: torch.Tensor       # int64 [n_tail_tiles + 1] tail postings, tile-major: first posting of a tile
-    tail_dir: torch.Tensor        # uint32 payload in int32 [n_tail_tiles, V + 1]: a term's range inside a tile
-    tail_post: torch.Tensor       # int32 [nnz_tail, 2]: (doc % tail_tile, weight bits), term-sorted inside a tile
-    tail_tile: int
+    tail: PostingsView            # tail terms only, no dense rows, tile_docs % 256 == 0
     head_dim: int
     n_terms: int
     n_docs: int
@@ -403,14 +400,13 @@ class SpladeHeadView:
     boot: "PostingsView | None" = None    # general index over the first boot.n_docs docs (threshold bootstrap)
 
     def nbytes(self) -> int:
-        return ((self.boot.nbytes() if self.boot is not None else 0) +
-                sum(t.numel() * t.element_size() for t in (self.head_bf16, self.term_head, self.term_max, self.tail_base, self.tail_dir, self.tail_post)))
+        return (self.tail.nbytes() + (self.boot.nbytes() if self.boot is not None else 0) +
+                sum(t.numel() * t.element_size() for t in (self.head_bf16, self.term_head, self.term_max)))
 
     def c_struct(self) -> _lib.SpladeHead:
         return _lib.SpladeHead(self.head_bf16.data_ptr(), self.term_head.data_ptr(), self.term_max.data_ptr(),
-                               self.doc_ptr.data_ptr(), self.doc_post.data_ptr(), self.tail_base.data_ptr(),
-                               self.tail_dir.data_ptr(), self.tail_post.data_ptr() if self.tail_post.numel() else 0,
-                               self.head_dim, self.n_terms, self.n_docs, 1 if self.unit_rows else 0, self.tail_tile)
+                               self.doc_ptr.data_ptr(), self.doc_post.data_ptr(), self.head_dim, self.n_terms, self.n_docs,
+                               1 if self.unit_rows else 0, 0)
 
 
 SPLADE_GROWTH = 2               # rounds grow 2x: a round emits the docs whose score UPPER BOUND beats the running k-th score
@@ -443,9 +439,9 @@ def splade_topk(index, q_ptr, q_term, q_weight, k: int, doc_base: int = 0, cap: 
     round_docs = max(256, min(int(max_round_docs), (hv.n_docs + 255) // 256 * 256))
     ws = _ws(lib.fz_splade_topk_workspace_bytes(nq, k_eff, cap, hv.head_dim, round_docs), dev)
     sc = _SyncCall(sync, nq, torch.float32, dev, k)
-    head = hv.c_struct()
+    tail, head = hv.tail.c_struct(), hv.c_struct()
     boot = hv.boot.c_struct() if hv.boot is not None else None
-    rc = lib.fz_splade_topk(C.byref(head), C.byref(boot) if boot is not None else None, _ptr(q_ptr), _ptr(q_term), _ptr(q_weight), nq, k_eff, doc_base, cap,
+    rc = lib.fz_splade_topk(C.byref(tail), C.byref(head), C.byref(boot) if boot is not None else None, _ptr(q_ptr), _ptr(q_term), _ptr(q_weight), nq, k_eff, doc_base, cap,
                             growth, _ptr(out_s), _ptr(out_i), _ptr(status), _ptr(ws), ws.numel(), sc.ref(), _stream(out_s))
     sc.reraise()
     check(rc, "fz_splade_topk")

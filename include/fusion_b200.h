@@ -262,9 +262,9 @@ int fz_sparse_scores_f32(const fz_postings_t* index, const int32_t* q_ptr, const
  * cosine of src/retrievers/hybrid.py:101-103 / splade/base.py:186-251, scores in fp32 to 1e-5 - for the queries it can serve.
  *
  * A Zipfian vocabulary puts > 95 % of all (query term, posting) pairs into the ~200 most frequent terms.  Those HEAD terms
- * are stored as a dense doc-major bf16 matrix and scored on the tensor cores (the K1 filter GEMM); the remaining TAIL terms'
- * sum is only needed as an upper bound, a 4-bit code per (query, doc), computed per (doc tile, block of 128 queries) from a
- * tile-major copy of the tail postings with a [tile][term] directory.  A doc whose head score + tail bound can still beat
+ * are stored as a dense doc-major bf16 matrix and scored on the tensor cores (the K1 filter GEMM); the remaining TAIL terms
+ * keep the inverted index (fz_postings_t built from the tail terms only, no dense rows, tile_docs % 256 == 0), but their
+ * sum is only needed as an upper bound: a 4-bit code per (query, doc).  A doc whose head score + tail bound can still beat
  * the query's running k-th EXACT score is appended to the candidate buffer and rescored exactly in fp32 from the doc-major
  * CSR copy; between rounds cand_select tightens the threshold on exact scores.  The returned scores are the exact ones.
  *   head_bf16 [n_docs, head_dim]: weight of head term j in doc d (bf16, row-major, head_dim % 64 == 0, 64..256)
@@ -283,20 +283,18 @@ typedef struct fz_splade_head {
     const float* term_max;
     const int64_t* doc_ptr;
     const void* doc_post;
-    const int64_t* tail_base;     /* [n_tail_tiles + 1] TAIL postings, tile-major (tiles of tail_tile docs): first posting of a tile */
-    const uint32_t* tail_dir;     /* [n_tail_tiles, n_terms + 1] range of a term's postings inside a tile, relative to tail_base */
-    const void* tail_post;        /* (uint32 doc % tail_tile, float weight) pairs, term-sorted inside a tile */
     int32_t head_dim;
     int32_t n_terms;
     int64_t n_docs;
     int32_t flags;                /* FZ_SPLADE_UNIT_ROWS: every doc vector has norm <= 1 (cos_sim index) */
-    int32_t tail_tile;            /* docs per tail tile: 256 .. 2048, a multiple of 256 */
+    int32_t reserved;
 } fz_splade_head_t;
 #define FZ_SPLADE_UNIT_ROWS 1
 
 /* max_round_docs bounds the code buffer (n_queries * max_round_docs / 2 bytes): rounds never span more documents */
 size_t fz_splade_topk_workspace_bytes(int n_queries, int k, int cap, int head_dim, int64_t max_round_docs);
-int fz_splade_topk(const fz_splade_head_t* head, const fz_postings_t* boot_index, const int32_t* q_ptr, const int32_t* q_term,
+int fz_splade_topk(const fz_postings_t* tail_index, const fz_splade_head_t* head, const fz_postings_t* boot_index,
+                   const int32_t* q_ptr, const int32_t* q_term,
                    const float* q_weight, int n_queries, int k, int64_t doc_base, int cap, int growth, float* out_scores,
                    int32_t* out_ids, int32_t* out_status, void* ws, size_t ws_bytes,
                    const fz_shard_sync_t* sync /* may be NULL */, fz_stream_t stream);

@@ -27,7 +27,7 @@ def test_splade_pipeline_vs_dense_oracle(head_dim):
     vocab, n_docs, nq, k = 2000, 6000, 12, 100
     dp, dt, dw = synth.splade_vectors(n_docs, vocab, 60, 8, 200, seed=311)
     qp, qt, qw = synth.splade_vectors(nq, vocab, 12, 2, 40, seed=312)
-    ix = SparseIndex(dp, dt, dw, vocab, "cos_sim", tile_docs=1024, tiled_min=64, head_dim=head_dim)
+    ix = SparseIndex(dp, dt, dw, vocab, "cos_sim", tile_docs=1024, tiled_min=64, head_dim=head_dim, tail_tile_docs=1024)
     assert ix.head is not None
     q_ptr, q_term, q_w = sparse_queries(qp, qt, qw, "cos_sim", ix.device)
     sc, ids = ops.splade_topk(ix, q_ptr, q_term, q_w, k, cap=512)
@@ -68,7 +68,7 @@ def test_splade_pipeline_fallback_few_matches_and_negative_weights():
     qw[qp[2]] = -qw[qp[2]]                    # one query with a negative weight
     qt = qt.copy()
     qt[qp[3]:qp[4]] = np.arange(vocab - (qp[4] - qp[3]), vocab)     # rare terms only: fewer than k matches
-    ix = SparseIndex(dp, dt, dw, vocab, "cos_sim", tile_docs=512, tiled_min=16, head_dim=64)
+    ix = SparseIndex(dp, dt, dw, vocab, "cos_sim", tile_docs=512, tiled_min=16, head_dim=64, tail_tile_docs=512)
     q_ptr, q_term, q_w = sparse_queries(qp, qt, qw, "dot", ix.device)
     sc, ids = ops.splade_topk(ix, q_ptr, q_term, q_w, k)
     sc2, ids2 = ops.sparse_topk(ix.view(), q_ptr, q_term, q_w, k)
@@ -83,14 +83,14 @@ def test_splade_pipeline_shards_with_cross_shard_floor():
     vocab, n_docs, nq, k, cap = 2000, 18000, 16, 100, 512
     dp, dt, dw = synth.splade_vectors(n_docs, vocab, 60, 8, 200, seed=311)
     qp, qt, qw = synth.splade_vectors(nq, vocab, 12, 2, 40, seed=312)
-    full = SparseIndex(dp, dt, dw, vocab, "cos_sim", head_dim=64)
+    full = SparseIndex(dp, dt, dw, vocab, "cos_sim", head_dim=64, tail_tile_docs=1024)
     q_ptr, q_term, q_w = sparse_queries(qp, qt, qw, "cos_sim", full.device)
     sc, ids = ops.splade_topk(full, q_ptr, q_term, q_w, k, cap=cap)
     kth = sc[:, -1].clone()
     parts = []
     for lo, hi in ((0, 6000), (6000, 12000), (12000, n_docs)):
         ix = SparseIndex(dp[lo:hi + 1] - dp[lo], dt[dp[lo]:dp[hi]], dw[dp[lo]:dp[hi]], vocab, "cos_sim", doc_base=lo,
-                         head_dim=64)
+                         head_dim=64, tail_tile_docs=1024)
         parts.append(ops.splade_topk(ix, q_ptr, q_term, q_w, k, doc_base=lo, cap=cap,
                                      sync=ops.ShardSync(lambda t: torch.minimum(t, kth, out=t), 3, 6000)))
     ms, mi = ops.merge_topk(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]), k)
