@@ -86,6 +86,7 @@ SIGNATURES = {
     "fz_dense_topk_filter": (_i, [_p, _p, _i, _i64, _i, _i, _f, _i64, _i, _i, _i, _p, _p, _p, _sz, _p, _p]),
     "fz_dense_topk_finish": (_i, [_p, _p, _p, _i, _i, _i, _i64, _i, _p, _p, _p, _p, _sz, _p]),
     "fz_dense_scores_f32": (_i, [_p, _p, _i, _i64, _i, _p, _p]),
+    "fz_pairwise_dot_f32": (_i, [_p, _p, _i64, _i, _p, _p]),
     "fz_normalize_rows": (_i, [_p, _i64, _i, _i, _p, _p, _p]),
     "fz_maxsim_workspace_bytes": (_sz, [_i, _i]),
     "fz_maxsim_pack": (_i, [_p, _p, _p, _i64, _p, _p]),

@@ -131,6 +131,19 @@ __global__ void __launch_bounds__(256) dense_scores_kernel(const float* __restri
         }
 }
 
+// ----------------------------------------------------------------------------------- row-wise dot products
+// out[i] = <Q[i,:], D[i,:]> in fp32 (compute_pairwise_similarity, src/retrievers/splade/base.py:173-184): one warp per row
+__global__ void pairwise_dot_kernel(const float* __restrict__ q, const float* __restrict__ d, long long n_rows, int dim,
+                                    float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n_rows) return;
+    float acc = 0.f;
+    for (int j = lane; j < dim; j += 32) acc = fmaf(q[(size_t)row * dim + j], d[(size_t)row * dim + j], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) out[row] = acc;
+}
+
 // ----------------------------------------------------------------------------------- row normalisation
 __global__ void normalize_rows_kernel(const float* __restrict__ x, long long n_rows, int dim, int normalize,
                                       float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16) {
@@ -292,6 +305,15 @@ int fz_dense_scores_f32(const float* q_f32, const float* d_f32, int n_queries, i
     if (n_queries == 0) return FZ_OK;
     dim3 grid((unsigned)ceil_div<long long>(n_docs, kFT), (unsigned)ceil_div(n_queries, kFT));
     dense_scores_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(q_f32, d_f32, n_queries, n_docs, dim, out_scores);
+    FZ_LAUNCH_CHECK();
+    return FZ_OK;
+}
+
+int fz_pairwise_dot_f32(const float* q_f32, const float* d_f32, int64_t n_rows, int dim, float* out, fz_stream_t stream) {
+    FZ_REQUIRE(q_f32 && d_f32 && out, "null pointer");
+    FZ_REQUIRE(dim >= 1, "bad dim");
+    if (n_rows == 0) return FZ_OK;
+    pairwise_dot_kernel<<<(unsigned)ceil_div<long long>(n_rows, 8), 256, 0, (cudaStream_t)stream>>>(q_f32, d_f32, n_rows, dim, out);
     FZ_LAUNCH_CHECK();
     return FZ_OK;
 }

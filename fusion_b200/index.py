@@ -209,6 +209,32 @@ class LexicalIndex:
         self._dl_values = torch.unique(self.doc_len).cpu().numpy().astype(np.float64)
         self.update_params(k1, b)
 
+    @classmethod
+    def from_postings(cls, term_ptr, post_doc, post_tf, doc_len, vocab_size: int, variant: str = "bm25", k1: float = 0.9,
+                      b: float = 0.4, device="cuda", doc_base: int = 0, tile_docs: int = LEX_TILE_DOCS,
+                      tiled_min: int | None = None, dense_frac: float = DENSE_FRAC):
+        """Rebuild the index from saved term-major CSR arrays (``BM25.load_indexes``): no tokenisation, no sort."""
+        if variant not in VARIANTS:
+            raise FusionB200Error(f"unknown lexical variant {variant!r}")
+        self = cls.__new__(cls)
+        self.variant, self.k1, self.b = variant, k1, b
+        self.device = torch.device(device)
+        self.vocab_size, self.doc_base, self.tile_docs = int(vocab_size), int(doc_base), int(tile_docs)
+        self.tiled_min, self.dense_frac = tiled_min, dense_frac
+        self.term_ptr = torch.as_tensor(np.asarray(term_ptr), dtype=torch.int64, device=self.device)
+        self.post_doc = torch.as_tensor(np.asarray(post_doc), dtype=torch.int32, device=self.device)
+        self.post_tf = torch.as_tensor(np.asarray(post_tf), dtype=torch.int32, device=self.device)
+        self.doc_len = torch.as_tensor(np.asarray(doc_len), dtype=torch.int32, device=self.device)
+        self.n_docs = self.doc_len.numel()
+        self.global_n_docs = self.n_docs
+        self.df = (self.term_ptr[1:] - self.term_ptr[:-1]).cpu().numpy()
+        sum_dl = int(self.doc_len.long().sum())
+        self.avgdl = float(Fraction(sum_dl, self.global_n_docs)) if self.global_n_docs else 0.0
+        self.idf = torch.from_numpy(idf_table(self.df, self.global_n_docs, variant)).to(self.device)
+        self._dl_values = torch.unique(self.doc_len).cpu().numpy().astype(np.float64)
+        self.update_params(k1, b)
+        return self
+
     def update_params(self, k1: float, b: float) -> None:
         """Recompute the per-posting fp64 impacts for new (k1, b) (bm25.py:158-161)."""
         self.k1, self.b = k1, b

@@ -575,6 +575,19 @@ def dense_scores(q_f32, d_f32):
     return out
 
 
+def pairwise_dot(q_f32, d_f32):
+    """Row-wise dot products of two [B, d] fp32 matrices -> fp32 [B]."""
+    lib = _lib.load()
+    q_f32 = _req(q_f32, torch.float32, "q_f32")
+    d_f32 = _req(d_f32, torch.float32, "d_f32")
+    if q_f32.shape != d_f32.shape:
+        raise FusionB200Error("pairwise similarity needs two matrices of the same shape")
+    out = torch.empty((q_f32.shape[0],), dtype=torch.float32, device=q_f32.device)
+    check(lib.fz_pairwise_dot_f32(_ptr(q_f32), _ptr(d_f32), q_f32.shape[0], q_f32.shape[1], _ptr(out), _stream(out)),
+          "fz_pairwise_dot_f32")
+    return out
+
+
 # ----------------------------------------------------------------------------------------------- K3
 def pack_tokens(tok_ptr: torch.Tensor, tok_emb_bf16: torch.Tensor):
     """Token store -> the packed image the MaxSim kernel streams (per passage two 64-dim halves of 128-byte rows, rows

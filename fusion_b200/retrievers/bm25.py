@@ -66,18 +66,22 @@ class TFIDF:
 
     @property
     def vocab(self):
+        self._need_string_vocab("vocab")
         return set(self._vocab)
 
     def get_vocab(self):
         """Return the vocabulary sorted by alphabetical order (bm25.py:48-50)."""
+        self._need_string_vocab("get_vocab")
         return sorted(self._vocab)
 
     @property
     def df(self):
+        self._need_string_vocab("df")
         return {w: int(self.index.df[t]) for w, t in self._vocab.items()}
 
     @property
     def idf(self):
+        self._need_string_vocab("idf")
         idf = self.index.idf.cpu().numpy()
         return {w: float(idf[t]) for w, t in self._vocab.items()}
 
@@ -148,14 +152,60 @@ class TFIDF:
             return 0.0
         return float(ops.sparse_scores(self.index.view(), q_ptr, q_term)[0, doc_idx])
 
-    def save_indexes(self, output_dir: str, dataset: str) -> None:
-        """Persist the index (bm25.py:117-126 pickles four dicts; here: vocabulary + CSR arrays in one .npz)."""
+    @property
+    def tf(self):
+        """``{word: {doc_idx: count}}`` like the reference's tf index (bm25.py:62-70), materialised from the device CSR."""
+        self._need_string_vocab("tf")
+        ix = self.index
+        ptr, doc, cnt = ix.term_ptr.cpu().numpy(), ix.post_doc.cpu().numpy(), ix.post_tf.cpu().numpy()
+        return {w: dict(zip(doc[ptr[t]:ptr[t + 1]].tolist(), cnt[ptr[t]:ptr[t + 1]].tolist())) for w, t in self._vocab.items()}
+
+    def _need_string_vocab(self, what: str) -> None:
+        if self._vocab is None:
+            raise ops.FusionB200Error(f"`{what}` needs the string vocabulary, which device_tokenizer=True does not keep "
+                                      "(the device vocabulary is a table of 128-bit token hashes)")
+
+    def _index_path(self, output_dir: str, dataset: str) -> str:
+        return os.path.join(output_dir, f'{self.__repr__()}_index_{dataset}.npz')
+
+    def save_indexes(self, output_dir: str, dataset: str, reference_pickles: bool = True) -> None:
+        """Save the indexes to disk (bm25.py:117-126).  Writes the reference's four pickles
+        ``<name>_{vocab,tf,df,idf}_<dataset>.pkl`` (a set, a dict of dicts, a Counter and a dict, like the reference's
+        attributes) and, next to them, ``<name>_index_<dataset>.npz``: the vocabulary and the CSR arrays
+        :meth:`load_indexes` restores the device index from without re-tokenising the corpus."""
+        import pickle
+        from collections import Counter
+        self._need_string_vocab("save_indexes")
         ix = self.index
         words = np.array(sorted(self._vocab, key=self._vocab.get))
-        np.savez_compressed(os.path.join(output_dir, f'{self.__repr__()}_index_{dataset}.npz'), vocab=words,
-                            term_ptr=ix.term_ptr.cpu().numpy(), post_doc=ix.post_doc.cpu().numpy(),
-                            post_tf=ix.post_tf.cpu().numpy(), doc_len=ix.doc_len.cpu().numpy(), df=ix.df,
-                            idf=ix.idf.cpu().numpy())
+        np.savez_compressed(self._index_path(output_dir, dataset), vocab=words, term_ptr=ix.term_ptr.cpu().numpy(),
+                            post_doc=ix.post_doc.cpu().numpy(), post_tf=ix.post_tf.cpu().numpy(),
+                            doc_len=ix.doc_len.cpu().numpy(), df=ix.df, idf=ix.idf.cpu().numpy(),
+                            params=np.array([getattr(self, "k1", 0.0), getattr(self, "b", 0.0)]))
+        if reference_pickles:
+            for name, obj in (("vocab", self.vocab), ("tf", self.tf), ("df", Counter(self.df)), ("idf", self.idf)):
+                with open(os.path.join(output_dir, f'{self.__repr__()}_{name}_{dataset}.pkl'), 'wb') as f:
+                    pickle.dump(obj, f)
+
+    @classmethod
+    def load_indexes(cls, output_dir: str, dataset: str, corpus: list[str] | None = None, device: str = "cuda", **kw):
+        """Restore a retriever saved by :meth:`save_indexes` (the reference has no loader: it rebuilds its dicts from the
+        corpus every run).  ``corpus`` is only kept for ``self.corpus``; the index comes from the file."""
+        g = np.load(os.path.join(output_dir, f'{cls.__name__.lower()}_index_{dataset}.npz'), allow_pickle=False)
+        self = cls.__new__(cls)
+        self.corpus = corpus
+        self._device_vocab = None
+        self._vocab = {str(w): i for i, w in enumerate(g["vocab"])}
+        k1, b = (float(x) for x in g["params"])
+        if cls._variant != "tfidf":
+            self.k1, self.b = kw.pop("k1", k1), kw.pop("b", b)
+        self.index = LexicalIndex.from_postings(g["term_ptr"], g["post_doc"], g["post_tf"], g["doc_len"], len(self._vocab),
+                                                variant=cls._variant, k1=getattr(self, "k1", 0.0), b=getattr(self, "b", 0.0),
+                                                device=device, **kw)
+        self.corpus_size = self.index.n_docs
+        self.doc_len = self.index.doc_len.cpu().tolist()
+        self.avgdl = self.index.avgdl
+        return self
 
 
 class BM25(TFIDF):

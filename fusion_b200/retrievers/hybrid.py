@@ -51,17 +51,21 @@ class Ranker:
 
     @staticmethod
     def bm25_search(queries: list[str], corpus: dict[int, str], do_preprocessing: bool, k1: float, b: float,
-                    return_topk: int = None, device: str = "cuda"):
-        """BM25 retrieval (hybrid.py:50-75): every document is ranked unless ``return_topk`` is given."""
+                    return_topk: int = None, device: str = "cuda", preprocessor=None):
+        """BM25 retrieval (hybrid.py:50-75): every document is ranked unless ``return_topk`` is given.
+
+        ``do_preprocessing``: the reference lemmatises with spaCy ``fr_core_news_md`` through its ``TextPreprocessor``
+        (src/data/preprocessor.py:15-39), a text pipeline outside the scoring path.  Pass an object with the same
+        ``preprocess(list[str], lemmatize=True) -> list[str]`` method as ``preprocessor``; without one, preprocessing
+        raises ImportError (as the reference does where spaCy is not installed)."""
         documents = list(corpus.values())
         idx2id = {i: pid for i, pid in enumerate(corpus.keys())}
         if do_preprocessing:
-            # the reference lemmatises with spaCy fr_core_news_md (src/data/preprocessor.py:15-39); that text
-            # pipeline is outside the scoring path and is only available where spaCy is installed
-            from src.data.preprocessor import TextPreprocessor  # noqa: F401  (raises ImportError like the reference)
-            cleaner = TextPreprocessor(spacy_model="fr_core_news_md")
-            documents = cleaner.preprocess(documents, lemmatize=True)
-            queries = cleaner.preprocess(queries, lemmatize=True)
+            if preprocessor is None:
+                raise ImportError("do_preprocessing=True needs a text preprocessor (the reference's spaCy TextPreprocessor, "
+                                  "src/data/preprocessor.py): pass it as `preprocessor=`")
+            documents = preprocessor.preprocess(documents, lemmatize=True)
+            queries = preprocessor.preprocess(queries, lemmatize=True)
         retriever = BM25(corpus=documents, k1=k1, b=b, device=device)
         scores, ids = retriever.search_all_tensors(queries, top_k=return_topk or len(documents))
         return [[{'corpus_id': idx2id.get(i), 'score': s} for i, s in zip(ri, rs)]
@@ -69,11 +73,15 @@ class Ranker:
 
     @staticmethod
     def _load_single_vector_model(model_name_or_path):
+        """An encoder object (anything with the reference's ``encode(sentences=, batch_size=, convert_to_tensor=,
+        show_progress_bar=[, query_mode=])``) is used as is.  A name is loaded with stock PyTorch / Hugging Face code:
+        SPLADE checkpoints through ``fusion_b200.retrievers.splade.SPLADE.from_pretrained`` (transformers masked-LM +
+        the CUDA activation head), bi-encoders through sentence-transformers when that package is installed."""
         if not isinstance(model_name_or_path, str):
-            return model_name_or_path                       # an object with .encode(...), e.g. a stock ST model
+            return model_name_or_path
         if 'splade' in model_name_or_path.lower():
-            from src.retrievers.splade.splade import SPLADE   # stock PyTorch encoder, not part of this package
-            return SPLADE(model_name_or_path, max_query_length=64, max_doc_length=512)
+            from .splade.splade import SPLADE
+            return SPLADE.from_pretrained(model_name_or_path, max_query_length=64, max_doc_length=512)
         from sentence_transformers import SentenceTransformer
         model = SentenceTransformer(model_name_or_path)
         model.max_seq_length = 512
@@ -182,12 +190,19 @@ def weight_grid(systems: list[str], step: float = 0.05) -> list[dict[str, float]
 
 def tune_linear_fusion_weights(results: dict[str, list[list[dict]]], labels: list[list[int]], normalization: str,
                                step: float = 0.05, percentile_distributions: dict | None = None,
-                               device: str = "cuda") -> list[dict]:
+                               device: str = "cuda", return_topk: int | None = 1000) -> list[dict]:
     """The linear-fusion weight sweep of ``hybrid.main`` (hybrid.py:404-426): one row per weight combination holding
     ``run_evaluation``'s metrics plus ``weight_<system>`` columns, in the reference's row order.  The reference fuses
     and evaluates once per combination (1,771 for four systems); here every system is normalised once and ONE kernel
-    evaluates all combinations per query (``fz_fuse_sweep``).  The ranked lists must be in descending score order."""
+    evaluates all combinations per query (``fz_fuse_sweep``).  The ranked lists must be in descending score order.
+
+    ``return_topk``: the reference calls ``Aggregator.fuse`` with its default ``return_topk=1000``, which slices the list of
+    QUERIES (hybrid.py:220), and ``run_evaluation`` zips predictions with labels - so with more than 1000 queries its
+    sweep evaluates the first 1000 only.  The default reproduces that; ``None`` evaluates every query."""
     systems = list(results.keys())
+    if return_topk is not None:
+        results = {s: r[:return_topk] for s, r in results.items()}
+        labels = labels[:return_topk]
     host = [_lists_to_tensors(results[s], device) for s in systems]
     lists = [(torch.from_numpy(h[0].astype(np.int32)).to(device), torch.from_numpy(h[1]).to(device),
               torch.from_numpy(h[2]).to(device)) for h in host]
@@ -221,6 +236,8 @@ class Aggregator:
             # the reference appends the untransformed lists when the method is unknown; sums of raw scores
             method, normalization, linear_weights = 'nsf', 'none', {s: 1.0 for s in ranked_lists}
         systems = list(ranked_lists.keys())
+        if num_queries == 0:
+            return []
         id_arrays, remap = [], None
         host = [_lists_to_tensors(ranked_lists[s], device) for s in systems]
         lo = min(int(h[0].min()) for h in host)

@@ -17,10 +17,10 @@ class BaseModel:
     similarity: str = "cos_sim"
 
     def compute_pairwise_similarity(self, q_embs: torch.Tensor, d_embs: torch.Tensor) -> torch.Tensor:
-        """[B, d] x [B, d] -> [B] (base.py:173-184): the diagonal of the batchwise matrix, on the GPU library."""
+        """[B, d] x [B, d] -> [B] (base.py:173-184): row-wise products, on the GPU library."""
         q32, _ = ops.normalize_rows(q_embs.float().cuda(), normalize=self.similarity == "cos_sim", want_bf16=False)
         d32, _ = ops.normalize_rows(d_embs.float().cuda(), normalize=self.similarity == "cos_sim", want_bf16=False)
-        return torch.diagonal(ops.dense_scores(q32, d32)).clone()
+        return ops.pairwise_dot(q32, d32)
 
     def compute_batchwise_similarity(self, q_embs: torch.Tensor, d_embs: torch.Tensor) -> torch.Tensor:
         """[Q, d] x [D, d] -> [Q, D] fp32 (base.py:186-197): optional L2 normalisation, exact fp32 products."""

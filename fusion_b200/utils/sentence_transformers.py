@@ -20,14 +20,25 @@ from ..retrievers.hybrid import Ranker
 logger = logging.getLogger(__name__)
 
 
+def _score_matrix(a, b, normalize: bool):
+    from .. import ops
+    a = torch.as_tensor(a).float().cuda()
+    b = torch.as_tensor(b).float().cuda()
+    a, b = (a[None] if a.dim() == 1 else a), (b[None] if b.dim() == 1 else b)
+    a32, _ = ops.normalize_rows(a, normalize=normalize, want_bf16=False)
+    b32, _ = ops.normalize_rows(b, normalize=normalize, want_bf16=False)
+    return ops.dense_scores(a32, b32)
+
+
 def cos_sim(a, b):
-    """name-compatible score function marker (sentence_transformers.util.cos_sim)"""
-    raise NotImplementedError("marker only: scoring runs in the CUDA library")
+    """``sentence_transformers.util.cos_sim``: [A, d] x [B, d] -> cosine matrix [A, B] (exact fp32, CUDA library).  Also
+    the key under which ``InformationRetrievalEvaluatorCustom`` selects cosine scoring."""
+    return _score_matrix(a, b, True)
 
 
 def dot_score(a, b):
-    """name-compatible score function marker (sentence_transformers.util.dot_score)"""
-    raise NotImplementedError("marker only: scoring runs in the CUDA library")
+    """``sentence_transformers.util.dot_score``: [A, d] x [B, d] -> dot-product matrix [A, B]."""
+    return _score_matrix(a, b, False)
 
 
 class InformationRetrievalEvaluatorCustom:

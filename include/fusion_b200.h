@@ -329,6 +329,8 @@ int fz_dense_topk_finish(const float* q_f32, const float* d_f32, const float* ta
 /* exact fp32 scores of every (query, doc) pair on CUDA cores: out [n_queries, n_docs] (full-ranking mode) */
 int fz_dense_scores_f32(const float* q_f32, const float* d_f32, int n_queries, int64_t n_docs, int dim,
                         float* out_scores, fz_stream_t stream);
+/* out[i] = <q[i,:], d[i,:]> (compute_pairwise_similarity, src/retrievers/splade/base.py:173-184) */
+int fz_pairwise_dot_f32(const float* q_f32, const float* d_f32, int64_t n_rows, int dim, float* out, fz_stream_t stream);
 /* rows / max(||row||, 1e-12) (torch.nn.functional.normalize, base.py:195-196); either output may be NULL;
  * normalize == 0 only converts. */
 int fz_normalize_rows(const float* x, int64_t n_rows, int dim, int normalize, float* out_f32, void* out_bf16,

@@ -70,3 +70,14 @@ def test_sparse_topk_shard_sync_is_inert_for_one_shard():
         raise AssertionError("expected the stored exception")
     except RuntimeError as e:
         assert "collective failed" in str(e)
+
+
+def test_package_never_imports_the_reference_tree():
+    """A drop-in replacement must not need /root/reference on sys.path: no `from src...` / `import src...` anywhere."""
+    import re
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "fusion_b200")
+    for dirpath, _, files in os.walk(root):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+src(\.|\s)", src, flags=re.M), os.path.join(dirpath, f)

@@ -130,3 +130,15 @@ def test_splade_head_matches_reference(golden_dir, pooling):
     dense[np.repeat(np.arange(len(ptr) - 1), np.diff(ptr)), term] = w
     assert np.array_equal(dense, g[f"act_{pooling}"]) and ptr[-1] == np.count_nonzero(dense)
     assert all(np.all(np.diff(term[ptr[i]:ptr[i + 1]]) > 0) for i in range(len(ptr) - 1))
+
+
+def test_maxsim_oracle_matches_independent_padded_fixture(golden_dir):
+    """colbert-ai is third-party and absent: ``oracle/maxsim.py`` (ragged per-pair loop) is pinned against the committed
+    fixture of ``oracle/make_golden_maxsim.py`` - colbert_score's padded-batch formulation (D_padded @ Q^T, padding rows
+    -> -9999, max over doc tokens, sum over query tokens) in float64, incl. an empty and a 1-token passage."""
+    import torch
+    from oracle import maxsim
+    g = np.load(os.path.join(golden_dir, "maxsim_small.npz"))
+    got = maxsim.maxsim_scores(torch.from_numpy(g["q"]), torch.from_numpy(g["tok_ptr"]), torch.from_numpy(g["tok_emb"]),
+                               torch.from_numpy(g["cand"])).numpy()
+    np.testing.assert_allclose(got, g["scores"], rtol=1e-6, atol=2e-6)
