@@ -10,7 +10,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libfusion_b200.so")
 
-FZ_STATUS_OVERFLOW, FZ_STATUS_NEED_ZERO, FZ_STATUS_NEED_NEG, FZ_STATUS_FALLBACK = 1, 2, 4, 8
+FZ_STATUS_OVERFLOW, FZ_STATUS_NEED_ZERO, FZ_STATUS_NEED_NEG, FZ_STATUS_FALLBACK, FZ_STATUS_TOO_LONG = 1, 2, 4, 8, 16
 FUSE_METHODS = {"bcf": 0, "rrf": 1, "nsf": 2}
 FUSE_NORMS = {None: 0, "none": 0, "min-max": 1, "z-score": 2, "arctan": 3, "percentile-rank": 4,
               "normal-curve-equivalent": 5, "identity-f32": 6}
@@ -64,7 +64,7 @@ SIGNATURES = {
     "fz_rank_rows_f64": (_i, [_p, _i, _i64, _i, _i64, _p, _p, _p, _sz, _p]),
     "fz_fuse_workspace_bytes": (_sz, [_i, _i, _p]),
     "fz_fuse": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _i, _p, _sz, _p]),
-    "fz_rank_metrics": (_i, [_p, _p, _i, _i, _p, _p, _p, _i, _p, _i, _p, _i, _p, _i, _p, _p]),
+    "fz_rank_metrics": (_i, [_p, _p, _i, _i, _p, _p, _p, _i, _p, _i, _p, _i, _p, _i, _p, _p, _p]),
     "fz_fuse_sweep": (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _i, _p, _p, _p, _i, _p, _i, _p, _i, _p, _i, _p, _p]),
     "fz_token_starts": (_i, [_p, _i64, _p, _p]),
     "fz_hash_tokens": (_i, [_p, _i64, _p, _i64, _p, _p, _p, _p]),
@@ -77,8 +77,8 @@ SIGNATURES = {
     "fz_sparse_topk_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "fz_sparse_topk_f64": (_i, [_p, _p, _p, _i, _i, _i64, _i, _i, _i, _p, _p, _p, _p, _sz, _p, _p]),
     "fz_sparse_topk_f32": (_i, [_p, _p, _p, _p, _i, _i, _i64, _i, _i, _i, _p, _p, _p, _p, _sz, _p, _p]),
-    "fz_sparse_scores_f64": (_i, [_p, _p, _p, _i, _p, _p]),
-    "fz_sparse_scores_f32": (_i, [_p, _p, _p, _p, _i, _p, _p]),
+    "fz_sparse_scores_f64": (_i, [_p, _p, _p, _i, _p, _i, _p]),
+    "fz_sparse_scores_f32": (_i, [_p, _p, _p, _p, _i, _p, _i, _p]),
     "fz_splade_topk_workspace_bytes": (_sz, [_i, _i, _i, _i, _i64]),
     "fz_splade_topk": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i64, _i, _i, _p, _p, _p, _p, _sz, _p, _p]),
     "fz_dense_topk_workspace_bytes": (_sz, [_i, _i, _i]),

@@ -31,6 +31,7 @@ struct FuseParams {
     double weight[FZ_FUSE_MAX_SYSTEMS];
     int n_sys, n_queries, method, norm;
     int keep_order;    // FZ_FUSE_KEEP_ORDER: one system, output in first-insertion order instead of sorted
+    int promote64;     // FZ_FUSE_PROMOTE_F64: fp32 normalised scores are weighted and summed in fp64 (NumPy 1.x promotion)
     int table_slots;   // power of two
     int max_len;       // longest list
     int use_smem;
@@ -265,13 +266,13 @@ __global__ void __launch_bounds__(kFuseThreads) fuse_kernel(const FuseParams P) 
                         }
                     }
                 }
-                v = (double)__fmul_rn(t, w32);
+                v = P.promote64 ? __dmul_rn((double)t, w64) : (double)__fmul_rn(t, w32);
             }
             if (h_order[slot] == 0xffffffffu) {
                 h_order[slot] = (uint32_t)(base_order + rank);
                 atomicAdd(&s_union, 1);
             }
-            if (f32_path)
+            if (f32_path && !P.promote64)
                 h_acc[slot] = (double)__fadd_rn((float)h_acc[slot], (float)v);
             else
                 h_acc[slot] = __dadd_rn(h_acc[slot], v);
@@ -477,7 +478,8 @@ int fz_fuse(const int32_t* const* ids_h, const void* const* scores_h, const int3
     FZ_REQUIRE(n_sys >= 1 && n_sys <= FZ_FUSE_MAX_SYSTEMS, "n_sys=%d must be in [1,%d]", n_sys, FZ_FUSE_MAX_SYSTEMS);
     FZ_REQUIRE(ids_h && scores_h && score_is_f64_h && list_stride_h && out_ids && out_scores && out_len, "null pointer");
     const int keep_order = (method & FZ_FUSE_KEEP_ORDER) != 0;
-    method &= ~FZ_FUSE_KEEP_ORDER;
+    const int promote64 = (method & FZ_FUSE_PROMOTE_F64) != 0;
+    method &= ~(FZ_FUSE_KEEP_ORDER | FZ_FUSE_PROMOTE_F64);
     FZ_REQUIRE(method == FZ_FUSE_BCF || method == FZ_FUSE_RRF || method == FZ_FUSE_NSF, "unknown fusion method %d", method);
     FZ_REQUIRE(!keep_order || n_sys == 1, "FZ_FUSE_KEEP_ORDER needs exactly one system");
     FZ_REQUIRE(out_stride >= 1, "out_stride must be positive");
@@ -508,6 +510,7 @@ int fz_fuse(const int32_t* const* ids_h, const void* const* scores_h, const int3
     P.n_queries = n_queries;
     P.method = method;
     P.keep_order = keep_order;
+    P.promote64 = promote64;
     P.norm = normalization;
     fuse_plan(n_sys, list_stride_h, &P.table_slots, &P.max_len, &P.ws_per_query);
     P.use_smem = P.ws_per_query <= kFuseSmemLimit;

@@ -18,7 +18,7 @@
 
 namespace fz {
 
-constexpr int kMaxGold = 64;      // gold documents per query
+constexpr int kMaxGold = 256;     // distinct gold documents per query (more: the outputs are poisoned with NaN, never truncated)
 constexpr int kMaxKs = 8;         // cut-offs per metric family
 constexpr int kMetricThreads = 256;
 constexpr int kSweepThreads = 512;
@@ -73,11 +73,13 @@ __device__ int load_gold(const int32_t* gold_ptr, const int32_t* gold_ids, int q
     const int b = gold_ptr[q], e = gold_ptr[q + 1];
     n_gold = e - b;
     int n = 0;
-    for (int i = b; i < e && n < kMaxGold; ++i) {
+    for (int i = b; i < e; ++i) {
         const int g = gold_ids[i];
         bool dup = false;
         for (int j = 0; j < n; ++j) dup |= s_gold[j] == g;
-        if (!dup) s_gold[n++] = g;
+        if (dup) continue;
+        if (n == kMaxGold) return -1;        // too many relevant docs for the shared-memory tables: the caller poisons the result
+        s_gold[n++] = g;
     }
     return n;
 }
@@ -94,7 +96,7 @@ __device__ void sort_ranks(int* r, int n) {      // insertion sort, n <= kMaxGol
 // ------------------------------------------------------------------------------------------ metrics of ranked lists
 __global__ void __launch_bounds__(kMetricThreads)
 rank_metrics_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ lens, int stride, const int32_t* gold_ptr,
-                    const int32_t* gold_ids, MetricCfg C, double* __restrict__ out_sum) {
+                    const int32_t* gold_ids, MetricCfg C, double* __restrict__ out_sum, double* __restrict__ per_query) {
     __shared__ int s_gold[kMaxGold], s_rank[kMaxGold];
     __shared__ int s_n, s_ngold;
     const int q = blockIdx.x;
@@ -106,6 +108,14 @@ rank_metrics_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__
     for (int i = threadIdx.x; i < kMaxGold; i += blockDim.x) s_rank[i] = kNoRank;
     __syncthreads();
     const int n = s_n;
+    if (n < 0) {            // more than kMaxGold distinct gold ids
+        if (threadIdx.x == 0)
+            for (int i = 0; i < C.count(); ++i) {
+                if (per_query) per_query[(size_t)q * C.count() + i] = nan("");
+                else atomicAdd(&out_sum[i], nan(""));
+            }
+        return;
+    }
     const int len = lens ? min(lens[q], stride) : stride;
     const int32_t* row = ids + (size_t)q * stride;
     for (int p = threadIdx.x; p < len; p += blockDim.x) {
@@ -115,14 +125,29 @@ rank_metrics_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__
             if (s_gold[j] == d) atomicMin(&s_rank[j], p + 1);      // a repeated id counts at its first position
     }
     __syncthreads();
-    if (threadIdx.x == 0 && s_ngold > 0) {
-        sort_ranks(s_rank, n);
-        int nf = 0;
-        while (nf < n && s_rank[nf] != kNoRank) ++nf;
+    if (threadIdx.x == 0) {
         double m[4 * kMaxKs + 1];
-        metrics_from_ranks(s_rank, nf, s_ngold, C, m);
-        for (int i = 0; i < C.count(); ++i) atomicAdd(&out_sum[i], m[i]);
+        for (int i = 0; i < C.count(); ++i) m[i] = 0.0;
+        if (s_ngold > 0) {
+            sort_ranks(s_rank, n);
+            int nf = 0;
+            while (nf < n && s_rank[nf] != kNoRank) ++nf;
+            metrics_from_ranks(s_rank, nf, s_ngold, C, m);
+        }
+        for (int i = 0; i < C.count(); ++i) {
+            if (per_query) per_query[(size_t)q * C.count() + i] = m[i];
+            else if (s_ngold > 0) atomicAdd(&out_sum[i], m[i]);
+        }
     }
+}
+
+// out_sum[m] = sum over the queries in query order: the same bits every run (statistics.mean-style accumulation order)
+__global__ void metrics_reduce_kernel(const double* __restrict__ per_query, int n_queries, int n_metrics, double* __restrict__ out_sum) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n_metrics) return;
+    double s = 0.0;
+    for (int q = 0; q < n_queries; ++q) s = __dadd_rn(s, per_query[(size_t)q * n_metrics + m]);
+    out_sum[m] = s;
 }
 
 // ------------------------------------------------------------------------------------------ weight sweep
@@ -143,16 +168,18 @@ __device__ __forceinline__ int sweep_hash(int key, int mask) {
     return (int)((((uint32_t)key * 2654435761u) >> 7) & (uint32_t)mask);
 }
 
-// fused score of one union entry: sum over the systems that hold it, in system order, fp32 (torch-normalised scores,
-// hybrid.py:291,302) or fp64 (normalization 'none')
+// fused score of one union entry: sum over the systems that hold it, in system order; fp32 (torch-normalised) or fp64
+// (normalization 'none') values, always weighted and summed in fp64
 template <bool F32>
 __device__ __forceinline__ double fused_score(const float* const* t32, const double* const* t64, uint32_t meta, int slot,
                                               const double* w, int n_sys) {
     if (F32) {
-        float a = 0.f;
+        // the sweep's weights come from np.arange: np.float64 scalars, so np.float32 score * weight is float64 under every
+        // NumPy version and aggregate_scores sums doubles (hybrid.py:291,302,405-409)
+        double a = 0.0;
         for (int s = 0; s < n_sys; ++s)
-            if (meta & (1u << (28 + s))) a = __fadd_rn(a, __fmul_rn(t32[s][slot], (float)w[s]));
-        return (double)a;
+            if (meta & (1u << (28 + s))) a = __dadd_rn(a, __dmul_rn((double)t32[s][slot], w[s]));
+        return a;
     }
     double a = 0.0;
     for (int s = 0; s < n_sys; ++s)
@@ -190,6 +217,11 @@ __global__ void __launch_bounds__(kSweepThreads) fuse_sweep_kernel(const SweepPa
         s_base = 0;
     }
     __syncthreads();
+    if (s_n < 0) {          // more than kMaxGold distinct gold ids: poison every row, never truncate
+        const int nm = P.cfg.count();
+        for (int i = threadIdx.x; i < P.n_weights * nm; i += blockDim.x) atomicAdd(&P.out_sum[i], nan(""));
+        return;
+    }
 
     // ---- union table: systems one after the other, so "first insertion" = (system order, rank inside the system)
     for (int s = 0; s < P.n_sys; ++s) {
@@ -308,7 +340,7 @@ extern "C" {
 int fz_rank_metrics(const int32_t* ids, const int32_t* lens, int n_queries, int stride, const int32_t* gold_ptr,
                     const int32_t* gold_ids, const int32_t* recall_k_h, int n_recall, const int32_t* map_k_h, int n_map,
                     const int32_t* mrr_k_h, int n_mrr, const int32_t* ndcg_k_h, int n_ndcg, double* out_sum,
-                    fz_stream_t stream_) {
+                    double* ws_per_query, fz_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     FZ_REQUIRE(ids && gold_ptr && gold_ids && out_sum, "null pointer");
     FZ_REQUIRE(stride >= 1 && n_queries >= 0, "bad sizes");
@@ -317,7 +349,8 @@ int fz_rank_metrics(const int32_t* ids, const int32_t* lens, int n_queries, int 
     if (rc) return rc;
     FZ_CUDA(cudaMemsetAsync(out_sum, 0, sizeof(double) * C.count(), stream));
     if (n_queries == 0) return FZ_OK;
-    rank_metrics_kernel<<<n_queries, kMetricThreads, 0, stream>>>(ids, lens, stride, gold_ptr, gold_ids, C, out_sum);
+    rank_metrics_kernel<<<n_queries, kMetricThreads, 0, stream>>>(ids, lens, stride, gold_ptr, gold_ids, C, out_sum, ws_per_query);
+    if (ws_per_query) metrics_reduce_kernel<<<1, 64, 0, stream>>>(ws_per_query, n_queries, C.count(), out_sum);
     FZ_LAUNCH_CHECK();
     return FZ_OK;
 }

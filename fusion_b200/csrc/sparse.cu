@@ -61,6 +61,7 @@ struct SparseArgs {
     int sign_mode;            // +1: emit score > 0, -1: emit score < 0
     CandState<AccT> st;
     AccT* out_full;           // full mode: [n_queries, n_docs]
+    int accumulate;           // full mode: start from the row's current values (later term chunks of queries > kMaxTerms terms)
     // zero-fill
     int k;
     long long doc_base;
@@ -138,7 +139,11 @@ __device__ __forceinline__ void resolve_terms(const SparseArgs<AccT>& A, int q, 
         S.kind[t] = kind;
         S.w[t] = w;
     }
-    if (t == 0) S.n = nt;
+    if (t == 0) {
+        S.n = nt;
+        // never truncate silently: the top-k entry points flag the query, the caller scores it in chunks (fz_sparse_scores_*)
+        if (A.q_ptr[q + 1] - qb > kMaxTerms && A.st.status) atomicOr(&A.st.status[q], FZ_STATUS_TOO_LONG);
+    }
 }
 
 // Accumulate one query's postings that fall into tile `tile` (docs [d_lo, d_lo + tile_docs)) into acc[0 .. tile_docs).
@@ -157,7 +162,8 @@ __device__ __forceinline__ void resolve_terms(const SparseArgs<AccT>& A, int q, 
 template <typename AccT, bool kToSmem>
 __device__ __forceinline__ void accumulate_tile(const SparseArgs<AccT>& A, int tile, long long d_lo, AccT* acc,
                                                 const TermStatic& S, TermList& L, uint32_t o0, uint32_t o1,
-                                                typename std::conditional<std::is_same<AccT, double>::value, double2, float4>::type (&racc)[kChunks]) {
+                                                typename std::conditional<std::is_same<AccT, double>::value, double2, float4>::type (&racc)[kChunks],
+                                                const AccT* __restrict__ init = nullptr, int n_init = 0) {
     constexpr int kVec = AccTraits<AccT>::kVec;
     constexpr bool kF64 = std::is_same<AccT, double>::value;
     using Vec = typename std::conditional<kF64, double2, float4>::type;
@@ -221,6 +227,15 @@ __device__ __forceinline__ void accumulate_tile(const SparseArgs<AccT>& A, int t
 #pragma unroll
     for (int c = 0; c < kChunks; ++c) {
         if constexpr (kF64) racc[c] = make_double2(0.0, 0.0); else racc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (init) {         // continue the sums of an earlier chunk of this query's terms (same left-to-right order)
+            AccT v[kVec];
+#pragma unroll
+            for (int u = 0; u < kVec; ++u) {
+                const int i = (c * T + t) * kVec + u;
+                v[u] = i < n_init ? init[i] : (AccT)0;
+            }
+            racc[c] = *reinterpret_cast<const Vec*>(v);
+        }
     }
     bool in_reg = true;       // the running sums of this thread's docs live in racc (shared memory is stale)
 
@@ -339,24 +354,11 @@ __global__ void __launch_bounds__(kMaxSparseThreads) sparse_tile_kernel(const Sp
         const long long d_lo = (long long)tile * A.ix.tile_docs;
         const long long d_hi = min(d_lo + A.ix.tile_docs, (long long)A.ix.n_docs);
         Vec racc[kChunks];
-        accumulate_tile<AccT, false>(A, tile, d_lo, acc, S, L[tile & 1], o0, o1, racc);
+        const bool cont = MODE == 1 && A.accumulate;
+        accumulate_tile<AccT, false>(A, tile, d_lo, acc, S, L[tile & 1], o0, o1, racc,
+                                     cont ? A.out_full + (size_t)q * A.ix.n_docs + d_lo : nullptr, (int)(d_hi - d_lo));
         o0 = o1;
         o1 = o2;
-#ifdef FZ_PREFETCH_SCATTER
-        // EXPERIMENTAL (build with FZ_PREFETCH_SCATTER=1, compiled out by default, not yet measured): pull the head of the
-        // NEXT tile's scatter segments into L1 while this tile is scanned.  A scatter phase waits for one L2 round trip to
-        // move a median of 23 (BM25) / 32 (SPLADE) postings; the term-holding lanes know the segment bounds one tile
-        // ahead, and a prefetch needs no register.
-        // fp64 (BM25) only: the fp32 kernel went from 40 to 48 registers with it (12 -> 10 CTAs per SM)
-        if (std::is_same<AccT, double>::value && tile + 1 < t_end && threadIdx.x < max(S.n, 1) &&
-            S.kind[threadIdx.x] == kKindTiled && o1 > o0) {
-            const long long p = S.base[threadIdx.x] + o0;
-            const char* vp = reinterpret_cast<const char*>(reinterpret_cast<const AccT*>(A.ix.tiled_val) + p);
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(A.ix.tiled_off + p));
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(vp));
-            if ((o1 - o0) * sizeof(AccT) > 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(vp + 128));
-        }
-#endif
         // every thread scans its own docs in registers; survivors are rare once tau has risen
         // (a tile that straddles a round boundary is accumulated by both rounds and emitted once: [e_lo, e_hi))
         const int e_lo = MODE == 1 ? 0 : (int)(max(d_lo, A.r_lo) - d_lo);
@@ -999,7 +1001,7 @@ int sparse_bootstrap_f32(const fz_postings_t* ix, const int32_t* q_ptr, const in
 
 template <typename AccT>
 static int sparse_scores(const fz_postings_t* ix, const int32_t* q_ptr, const int32_t* q_term, const float* q_weight,
-                         int n_queries, AccT* out, cudaStream_t stream) {
+                         int n_queries, AccT* out, int accumulate, cudaStream_t stream) {
     int rc = check_index<AccT>(ix);
     if (rc) return rc;
     FZ_REQUIRE(q_ptr && q_term && out, "null pointer");
@@ -1014,6 +1016,7 @@ static int sparse_scores(const fz_postings_t* ix, const int32_t* q_ptr, const in
     A.q_weight = q_weight;
     A.n_queries = n_queries;
     A.out_full = out;
+    A.accumulate = accumulate;
     A.tile_lo = 0;
     A.tile_hi = ix->n_tiles;
     A.group_lo = 0;
@@ -1065,13 +1068,13 @@ int fz_sparse_topk_f32(const fz_postings_t* index, const int32_t* q_ptr, const i
 }
 
 int fz_sparse_scores_f64(const fz_postings_t* index, const int32_t* q_ptr, const int32_t* q_term, int n_queries,
-                         double* out_scores, fz_stream_t stream) {
-    return sparse_scores<double>(index, q_ptr, q_term, nullptr, n_queries, out_scores, (cudaStream_t)stream);
+                         double* out_scores, int accumulate, fz_stream_t stream) {
+    return sparse_scores<double>(index, q_ptr, q_term, nullptr, n_queries, out_scores, accumulate, (cudaStream_t)stream);
 }
 
 int fz_sparse_scores_f32(const fz_postings_t* index, const int32_t* q_ptr, const int32_t* q_term, const float* q_weight,
-                         int n_queries, float* out_scores, fz_stream_t stream) {
-    return sparse_scores<float>(index, q_ptr, q_term, q_weight, n_queries, out_scores, (cudaStream_t)stream);
+                         int n_queries, float* out_scores, int accumulate, fz_stream_t stream) {
+    return sparse_scores<float>(index, q_ptr, q_term, q_weight, n_queries, out_scores, accumulate, (cudaStream_t)stream);
 }
 
 }  // extern "C"

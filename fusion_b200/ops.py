@@ -12,7 +12,8 @@ from dataclasses import dataclass
 import torch
 
 from . import _lib
-from ._lib import FZ_STATUS_FALLBACK, FZ_STATUS_NEED_NEG, FZ_STATUS_OVERFLOW, FusionB200Error, check
+from ._lib import (FZ_STATUS_FALLBACK, FZ_STATUS_NEED_NEG, FZ_STATUS_OVERFLOW, FZ_STATUS_TOO_LONG, FusionB200Error,
+                   check)
 
 DEFAULT_CAP = 8192
 COARSE_TILES = 16          # FZ_COARSE_TILES
@@ -78,13 +79,15 @@ def rank_rows(scores: torch.Tensor, k: int, doc_base: int = 0, max_ws_bytes: int
 
 # ----------------------------------------------------------------------------------------------- K4
 def fuse(lists, method: str, normalization: str | None = None, weights=None, distributions=None,
-         out_stride: int | None = None, max_ws_bytes: int = 2 << 30, keep_order: bool = False):
+         out_stride: int | None = None, max_ws_bytes: int = 2 << 30, keep_order: bool = False, promote_f64: bool = False):
     """Fuse ``S`` ranked-list systems.
 
     lists: sequence of (ids int32 [Q, n_s], scores f32|f64 [Q, n_s], lens int32 [Q] | None), rank order.
     -> (ids int32 [Q, U], scores f64 [Q, U], lens int32 [Q]); U = out_stride or sum(n_s).  Rows are the union of
     the lists, fused score descending, ties by first insertion; padded with (-1, -inf).  ``keep_order`` (one system
-    only) returns the transformed, deduplicated list in first-insertion order instead.
+    only) returns the transformed, deduplicated list in first-insertion order instead.  ``promote_f64`` (nsf with a torch
+    normalisation): weight and sum the fp32 normalised scores in fp64 - NumPy 1.x's ``np.float32 * float`` - instead of fp32
+    (NumPy >= 2, NEP 50).
     """
     lib = _lib.load()
     if method not in _lib.FUSE_METHODS:
@@ -133,7 +136,7 @@ def fuse(lists, method: str, normalization: str | None = None, weights=None, dis
         check(lib.fz_fuse(
             arr_p(*[t[lo:hi].data_ptr() for t in ids_t]), arr_p(*[t[lo:hi].data_ptr() for t in sc_t]),
             arr_p(*[0 if t is None else t[lo:hi].data_ptr() for t in len_t]), arr_i(*is64), stride_arr, s, hi - lo,
-            _lib.FUSE_METHODS[method] | (0x100 if keep_order else 0), norm_code, arr_d(*w),
+            _lib.FUSE_METHODS[method] | (0x100 if keep_order else 0) | (0x200 if promote_f64 else 0), norm_code, arr_d(*w),
             arr_p(*[d.data_ptr() for d in distr_t]) if need_distr else None,
             arr_i(*[d.numel() for d in distr_t]) if need_distr else None,
             _ptr(out_ids[lo:hi]), _ptr(out_sc[lo:hi]), _ptr(out_len[lo:hi]), u, _ptr(ws), ws.numel(), _stream(out_ids)),
@@ -159,6 +162,15 @@ def _ks(*lists):
     return out
 
 
+MAX_GOLD_PER_QUERY = 256      # kMaxGold in csrc/metrics.cu
+
+
+def _check_gold_limit(out: torch.Tensor) -> None:
+    if bool(torch.isnan(out).any()):
+        raise FusionB200Error(f"a query has more than {MAX_GOLD_PER_QUERY} distinct relevant documents: the device metric "
+                              "kernels hold a query's gold ids in shared memory (the result would be wrong, not truncated)")
+
+
 def rank_metrics(ids: torch.Tensor, lens: torch.Tensor | None, gold_ptr: torch.Tensor, gold_ids: torch.Tensor,
                  recall_ks=RECALL_KS, map_ks=MAP_KS, mrr_ks=MRR_KS, ndcg_ks=NDCG_KS) -> torch.Tensor:
     """Mean retrieval metrics of ranked id lists [Q, n] against gold id lists (CSR) -> float64 [M], ``metric_names`` order
@@ -172,8 +184,10 @@ def rank_metrics(ids: torch.Tensor, lens: torch.Tensor | None, gold_ptr: torch.T
     q, n = ids.shape
     m = len(recall_ks) + len(map_ks) + len(mrr_ks) + len(ndcg_ks) + 1
     out = torch.empty(m, dtype=torch.float64, device=ids.device)
+    per_q = torch.empty((max(q, 1), m), dtype=torch.float64, device=ids.device)       # summed in query order: reproducible bits
     check(lib.fz_rank_metrics(_ptr(ids), _ptr(lens), q, n, _ptr(gold_ptr), _ptr(gold_ids), *_ks(recall_ks, map_ks, mrr_ks, ndcg_ks),
-                              _ptr(out), _stream(ids)), "fz_rank_metrics")
+                              _ptr(out), _ptr(per_q), _stream(ids)), "fz_rank_metrics")
+    _check_gold_limit(out)
     return out / max(q, 1)
 
 
@@ -206,6 +220,7 @@ def fuse_sweep(lists, normalization: str | None, weights: torch.Tensor, gold_ptr
                             arr_p(*[t.data_ptr() for t in norm[2]]), arr_i(*[t.shape[1] for t in norm[0]]), s, q, f32_path,
                             _ptr(weights), weights.shape[0], _ptr(gold_ptr), _ptr(gold_ids),
                             *_ks(recall_ks, map_ks, mrr_ks, ndcg_ks), _ptr(out), _stream(out)), "fz_fuse_sweep")
+    _check_gold_limit(out)
     return out / max(q, 1)
 
 
@@ -297,10 +312,29 @@ class _SyncCall:
             raise self.error
 
 
-def _check_query_lengths(q_ptr: torch.Tensor) -> None:
-    if q_ptr.numel() > 1 and int((q_ptr[1:] - q_ptr[:-1]).max()) > MAX_QUERY_TERMS:
-        raise FusionB200Error(f"a query has more than {MAX_QUERY_TERMS} terms (tokens, duplicates counted); "
-                              "the inverted-index kernels hold a query's terms in shared memory")
+FULL_ROWS_MAX_BYTES = 4 << 30         # score rows materialised for queries longer than MAX_QUERY_TERMS
+
+
+def _long_queries(q_ptr: torch.Tensor) -> torch.Tensor:
+    """Indices of the queries with more than MAX_QUERY_TERMS terms (tokens, duplicates counted); usually empty."""
+    if q_ptr.numel() <= 1:
+        return torch.zeros(0, dtype=torch.long, device=q_ptr.device)
+    return torch.nonzero((q_ptr[1:] - q_ptr[:-1]) > MAX_QUERY_TERMS).flatten()
+
+
+def _long_query_topk(pv: "PostingsView", q_ptr, q_term, q_weight, sel, k: int, doc_base: int):
+    """Queries longer than the kernels' per-CTA term table: score every document in chunks of MAX_QUERY_TERMS terms
+    (``sparse_scores`` continues the sums in query order, bit-identical to one pass) and rank the rows.  The reference has
+    no length limit (bm25.py:149-156 loops over query.split()); long legal questions and unpruned SPLADE queries reach it."""
+    per_q = pv.n_docs * pv.post_val.element_size()
+    step = max(1, FULL_ROWS_MAX_BYTES // max(per_q, 1))
+    out_s, out_i = [], []
+    for lo in range(0, sel.numel(), step):
+        p2, t2, w2 = _subset_queries(q_ptr, q_term, q_weight, sel[lo:lo + step])
+        s2, i2 = rank_rows(sparse_scores(pv, p2, t2, w2), k, doc_base)
+        out_s.append(s2)
+        out_i.append(i2)
+    return torch.cat(out_s), torch.cat(out_i)
 
 
 def _sparse_topk_once(pv: PostingsView, q_ptr, q_term, q_weight, k, doc_base, cap, growth, sign_mode, sync=None,
@@ -356,11 +390,17 @@ def sparse_topk(pv: PostingsView, q_ptr, q_term, q_weight, k: int, doc_base: int
     q_term = _req(q_term, torch.int32, "q_term")
     if q_weight is not None:
         q_weight = _req(q_weight, torch.float32, "q_weight")
-    _check_query_lengths(q_ptr)
     k_eff = min(k, pv.n_docs)
     cap = max(cap, 2 * k_eff)
     out_s, out_i, status = _sparse_topk_once(pv, q_ptr, q_term, q_weight, k_eff, doc_base, cap, growth, +1, sync, k)
     st = status.cpu()
+    too_long = (st & FZ_STATUS_TOO_LONG) != 0
+    if bool(too_long.any()):        # rare: more terms than a CTA holds - every document scored in term chunks, rows ranked
+        sel = torch.nonzero(too_long).flatten()
+        s2, i2 = _long_query_topk(pv, q_ptr, q_term, q_weight, sel, k_eff, doc_base)
+        seld = sel.to(out_s.device)
+        out_s[seld], out_i[seld] = s2, i2
+        st[sel] = 0
     over = (st & FZ_STATUS_OVERFLOW) != 0
     if bool(over.any()):            # rare: redo those queries with rounds that cannot overflow
         sel = torch.nonzero(over).flatten()
@@ -426,7 +466,6 @@ def splade_topk(index, q_ptr, q_term, q_weight, k: int, doc_base: int = 0, cap: 
     q_term = _req(q_term, torch.int32, "q_term")
     if q_weight is not None:
         q_weight = _req(q_weight, torch.float32, "q_weight")
-    _check_query_lengths(q_ptr)
     dev = hv.head_bf16.device
     nq = q_ptr.numel() - 1
     k_eff = min(k, hv.n_docs)
@@ -446,6 +485,7 @@ def splade_topk(index, q_ptr, q_term, q_weight, k: int, doc_base: int = 0, cap: 
     sc.reraise()
     check(rc, "fz_splade_topk")
     bad = (status & (FZ_STATUS_OVERFLOW | FZ_STATUS_FALLBACK)) != 0
+    bad[_long_queries(q_ptr)] = True       # more terms than the kernels' per-query tables: the general path scores them in chunks
     if bool(bad.any()):
         sel = torch.nonzero(bad).flatten()
         p2, t2, w2 = _subset_queries(q_ptr, q_term, q_weight, sel)
@@ -455,23 +495,40 @@ def splade_topk(index, q_ptr, q_term, q_weight, k: int, doc_base: int = 0, cap: 
 
 
 def sparse_scores(pv: PostingsView, q_ptr, q_term, q_weight=None):
-    """Score of every document for every query: [Q, n_docs] (fp64 for lexical impacts, fp32 for SPLADE weights)."""
+    """Score of every document for every query: [Q, n_docs] (fp64 for lexical impacts, fp32 for SPLADE weights).
+    Queries of more than MAX_QUERY_TERMS terms are scored in several passes over chunks of their terms; every pass
+    continues the row's sums in query order, so the result is bit-identical to one pass over all terms."""
     lib = _lib.load()
     q_ptr = _req(q_ptr, torch.int32, "q_ptr")
     q_term = _req(q_term, torch.int32, "q_term")
-    _check_query_lengths(q_ptr)
+    if q_weight is not None:
+        q_weight = _req(q_weight, torch.float32, "q_weight")
     nq = q_ptr.numel() - 1
     f64 = pv.dtype == torch.float64
     out = torch.empty((nq, pv.n_docs), dtype=pv.dtype, device=pv.term_ptr.device)
     st = pv.c_struct()
-    if f64:
-        check(lib.fz_sparse_scores_f64(C.byref(st), _ptr(q_ptr), _ptr(q_term), nq, _ptr(out), _stream(out)),
-              "fz_sparse_scores_f64")
-    else:
-        if q_weight is not None:
-            q_weight = _req(q_weight, torch.float32, "q_weight")
-        check(lib.fz_sparse_scores_f32(C.byref(st), _ptr(q_ptr), _ptr(q_term), _ptr(q_weight), nq, _ptr(out),
-                                       _stream(out)), "fz_sparse_scores_f32")
+    max_len = int((q_ptr[1:] - q_ptr[:-1]).max()) if nq else 0
+    n_pass = max(1, -(-max_len // MAX_QUERY_TERMS))
+    for p in range(n_pass):
+        if n_pass == 1:
+            ptr_p, term_p, w_p = q_ptr, q_term, q_weight
+        else:       # pass p: terms [128 p, 128 (p + 1)) of every query (empty for the short ones)
+            lens = (q_ptr[1:] - q_ptr[:-1]).long()
+            lo = torch.clamp(lens, max=p * MAX_QUERY_TERMS)
+            hi = torch.clamp(lens, max=(p + 1) * MAX_QUERY_TERMS)
+            cnt = hi - lo
+            ptr_p = torch.zeros(nq + 1, dtype=torch.int32, device=q_ptr.device)
+            ptr_p[1:] = torch.cumsum(cnt, 0).to(torch.int32)
+            row = torch.repeat_interleave(torch.arange(nq, device=q_ptr.device), cnt)
+            pos = torch.arange(int(cnt.sum()), device=q_ptr.device) - ptr_p[:-1].long()[row] + lo[row] + q_ptr[:-1].long()[row]
+            term_p = q_term[pos].contiguous() if pos.numel() else torch.full((1,), -1, dtype=torch.int32, device=q_ptr.device)
+            w_p = None if q_weight is None else (q_weight[pos].contiguous() if pos.numel() else torch.zeros(1, device=q_ptr.device))
+        if f64:
+            check(lib.fz_sparse_scores_f64(C.byref(st), _ptr(ptr_p), _ptr(term_p), nq, _ptr(out), 1 if p else 0, _stream(out)),
+                  "fz_sparse_scores_f64")
+        else:
+            check(lib.fz_sparse_scores_f32(C.byref(st), _ptr(ptr_p), _ptr(term_p), _ptr(w_p), nq, _ptr(out), 1 if p else 0,
+                                           _stream(out)), "fz_sparse_scores_f32")
     return out
 
 

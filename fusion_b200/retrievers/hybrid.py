@@ -226,8 +226,14 @@ class Aggregator:
     @classmethod
     def fuse(cls, ranked_lists: dict[str, list[list[dict]]], method: str, normalization: str = None,
              linear_weights: dict[str, float] = None, percentile_distributions: dict[str, np.array] = None,
-             return_topk: int = 1000, device: str = "cuda") -> list[dict[int, float]]:
-        """Fuse the ranked lists of different retrieval systems (hybrid.py:170-220)."""
+             return_topk: int = 1000, device: str = "cuda", numpy_promotion: str | None = None) -> list[dict[int, float]]:
+        """Fuse the ranked lists of different retrieval systems (hybrid.py:170-220).
+
+        ``numpy_promotion``: ``weight_scores`` multiplies the np.float32 normalised scores by the Python-float weights
+        (hybrid.py:291) and ``aggregate_scores`` sums them.  Under NumPy >= 2 (NEP 50) that stays float32; under the
+        NumPy 1.x the reference pins it promotes to float64, which can order near-tied fused scores differently.
+        ``"nep50"`` / ``"legacy"`` select the behaviour; the default follows the NumPy installed next to this package, i.e.
+        what the reference itself would compute in the same environment."""
         num_queries = len(next(iter(ranked_lists.values())))
         assert all(len(system_res) == num_queries for system_res in ranked_lists.values()), (
             "Ranked results from different retrieval systems have varying lenghts across systems (i.e., some systems have been run on more queries)."
@@ -254,9 +260,14 @@ class Aggregator:
             weights = [linear_weights[s] for s in systems]
             if normalization in ('percentile-rank', 'normal-curve-equivalent'):
                 distrs = [np.asarray(percentile_distributions.get(s), dtype=np.float64) for s in systems]
-        ids, scores, lens = ops.fuse(lists, method, normalization, weights, distrs)
-        fp32 = method == 'nsf' and normalization not in (None, 'none') and normalization in (
-            'min-max', 'z-score', 'arctan', 'percentile-rank', 'normal-curve-equivalent')
+        if numpy_promotion is None:
+            numpy_promotion = "nep50" if type(np.float32(1) * 1.0) is np.float32 else "legacy"
+        if numpy_promotion not in ("nep50", "legacy"):
+            raise ValueError("numpy_promotion must be 'nep50' or 'legacy'")
+        torch_norm = method == 'nsf' and normalization in ('min-max', 'z-score', 'arctan', 'percentile-rank', 'normal-curve-equivalent')
+        ids, scores, lens = ops.fuse(lists, method, normalization, weights, distrs,
+                                     promote_f64=torch_norm and numpy_promotion == "legacy")
+        fp32 = torch_norm and numpy_promotion == "nep50"
         if remap is not None:
             ids = torch.from_numpy(remap[ids.cpu().numpy().clip(min=0)])
         final_results = _tensors_to_lists(ids, scores, lens, cast=np.float32 if fp32 else float)

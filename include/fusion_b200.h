@@ -45,6 +45,7 @@ int fz_debug_set_stats(void* device_buffer);
 #define FZ_STATUS_OVERFLOW 1  /* candidate buffer overflowed: result for this query is NOT valid, re-run with growth=1 */
 #define FZ_STATUS_NEED_ZERO 2 /* fewer than k positive-score docs: zero-score docs were appended in doc-id order */
 #define FZ_STATUS_NEED_NEG 4  /* positives + zero-score docs < k: negative-score docs are missing from the tail */
+#define FZ_STATUS_TOO_LONG 16 /* the query has more than FZ_MAX_QUERY_TERMS terms: result NOT valid (see fz_sparse_scores_*) */
 #define FZ_STATUS_FALLBACK 8  /* fz_splade_topk only: this query is outside the fast path's contract (negative weights, fewer than
                                 k positive-score docs, a tail sum outside the code range): re-run it with fz_sparse_topk_f32 */
 
@@ -86,6 +87,10 @@ int fz_rank_rows_f64(const double* scores, int n_queries, int64_t n_docs, int k,
 #define FZ_FUSE_NSF 2
 #define FZ_FUSE_KEEP_ORDER 0x100 /* OR into `method`, one system only: the transformed, deduplicated list in first-insertion
                                   order instead of sorted (the per-system normalisation step of fz_fuse_sweep) */
+#define FZ_FUSE_PROMOTE_F64 0x200 /* OR into `method` (nsf with a torch normalisation): weight and sum the fp32 normalised scores
+                                  in fp64.  weight_scores / aggregate_scores (hybrid.py:283-307) compute np.float32 * python
+                                  float: float32 under NumPy >= 2 (NEP 50, the default here), float64 under the NumPy 1.x the
+                                  reference pins */
 #define FZ_NORM_NONE 0
 #define FZ_NORM_MINMAX 1
 #define FZ_NORM_ZSCORE 2
@@ -108,8 +113,11 @@ int fz_fuse(const int32_t* const* ids_h, const void* const* scores_h, const int3
  * the queries (divide by n_queries for Metrics.compute_all_metrics, src/utils/metrics.py:40-162; the metric set of
  * run_evaluation, src/retrievers/hybrid.py:24-27, is recall {5,10,20,50,100,200,500,1000}, map/mrr/ndcg {10,100}).
  *   ids [n_queries, stride] (-1 padded), lens [n_queries] or NULL, gold_ptr [n_queries + 1], gold_ids: device memory
- *   *_k_h: host arrays of cut-offs (at most 8 each); at most 64 distinct gold ids per query are used
+ *   *_k_h: host arrays of cut-offs (at most 8 each); a query with more than 256 distinct gold ids turns the outputs into
+ *   NaN (never truncated silently)
  *   out_sum: device doubles [n_recall + n_map + n_mrr + n_ndcg + 1] in that order, R-precision last
+ *   ws_per_query: device doubles [n_queries, n_metrics] or NULL; with it the per-query values are summed in query order
+ *   (bit-reproducible), without it by atomics in arbitrary order
  * fz_fuse_sweep: the linear-fusion weight sweep of src/retrievers/hybrid.py:404-426 - for every weight vector, fuse the
  * systems' lists by weighted sum (union, missing = 0, stable descending order) and evaluate; out_sum [n_weights, M].
  *   ids_h[s] / vals_h[s]: host arrays of device pointers to the ALREADY NORMALISED lists [n_queries, list_stride[s]] without
@@ -120,7 +128,7 @@ int fz_fuse(const int32_t* const* ids_h, const void* const* scores_h, const int3
 int fz_rank_metrics(const int32_t* ids, const int32_t* lens, int n_queries, int stride, const int32_t* gold_ptr,
                     const int32_t* gold_ids, const int32_t* recall_k_h, int n_recall, const int32_t* map_k_h, int n_map,
                     const int32_t* mrr_k_h, int n_mrr, const int32_t* ndcg_k_h, int n_ndcg, double* out_sum,
-                    fz_stream_t stream);
+                    double* ws_per_query, fz_stream_t stream);
 int fz_fuse_sweep(const int32_t* const* ids_h, const double* const* vals_h, const int32_t* const* lens_h,
                   const int32_t* list_stride_h, int n_sys, int n_queries, int values_are_f32, const double* weights,
                   int n_weights, const int32_t* gold_ptr, const int32_t* gold_ids, const int32_t* recall_k_h, int n_recall,
@@ -237,7 +245,9 @@ int fz_lexical_impacts(const int64_t* term_ptr, const int32_t* post_doc, const i
 
 /* top-k: out [n_queries, k] (score desc, ties by lower doc id); zero-score docs fill up in doc-id order.
  *   q_ptr [n_queries+1], q_term [nq] (term ids in query-token order, duplicates kept, -1 = out of vocabulary;
- *   at most FZ_MAX_QUERY_TERMS per query - further terms are ignored, the caller must check),
+ *   at most FZ_MAX_QUERY_TERMS per query: a longer query gets FZ_STATUS_TOO_LONG in out_status and an unspecified row -
+ *   never a silently truncated score; score it with fz_sparse_scores_* in chunks of FZ_MAX_QUERY_TERMS terms
+ *   (accumulate = 1 from the second chunk on) + fz_rank_rows_*),
  *   q_weight [nq] float (f32 variant only; NULL => 1)
  *   growth: >= 2 geometric round growth (fast path), 1 = conservative rounds that can never overflow
  *   out_status [n_queries]: FZ_STATUS_* bits                                                              */
@@ -250,11 +260,13 @@ int fz_sparse_topk_f32(const fz_postings_t* index, const int32_t* q_ptr, const i
                        int n_queries, int k, int64_t doc_base, int cap, int growth, int sign_mode, float* out_scores,
                        int32_t* out_ids, int32_t* out_status, void* ws, size_t ws_bytes,
                        const fz_shard_sync_t* sync /* may be NULL */, fz_stream_t stream);
-/* every document's score: out [n_queries, n_docs] (full-ranking mode and tests) */
+/* every document's score: out [n_queries, n_docs] (full-ranking mode and tests).  accumulate != 0: the rows already hold the
+ * sums of the query's EARLIER terms and this call continues them in the same left-to-right order - how a query of more than
+ * FZ_MAX_QUERY_TERMS terms is scored in several calls (bit-identical to one pass over all its terms) */
 int fz_sparse_scores_f64(const fz_postings_t* index, const int32_t* q_ptr, const int32_t* q_term, int n_queries,
-                         double* out_scores, fz_stream_t stream);
+                         double* out_scores, int accumulate, fz_stream_t stream);
 int fz_sparse_scores_f32(const fz_postings_t* index, const int32_t* q_ptr, const int32_t* q_term, const float* q_weight,
-                         int n_queries, float* out_scores, fz_stream_t stream);
+                         int n_queries, float* out_scores, int accumulate, fz_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * K2c  SPLADE top-k as head GEMM + tail bound + exact rescoring (non-negative weights: SPLADE activations are

@@ -66,7 +66,9 @@ def test_dense_topk_exact_vs_oracle(nq, n_docs, dim, k):
 
 
 def test_dense_topk_bf16_mode_overlap():
-    """bf16 throughput mode: scores within 2e-3 relative, top-k overlap >= 99% excluding near-ties at the cut."""
+    """bf16 throughput mode (north-star): scores within 2e-3, top-k overlap >= 99.9 % excluding ties at the cutoff.  A tie
+    in this mode is a reference score within the stated bf16 score tolerance (2e-3 relative) of the k-th one: two documents
+    closer than the arithmetic's resolution cannot be ordered by it."""
     from fusion_b200.retrievers.hybrid import Ranker
     nq, n_docs, dim, k = 64, 50000, 768, 100
     q = torch.from_numpy(synth.dense_embeddings(nq, dim, seed=61))
@@ -77,7 +79,7 @@ def test_dense_topk_bf16_mode_overlap():
     hit = tot = 0
     for qi in range(nq):
         cut = float(esc[qi, -1])
-        b = {int(i) for i, s in zip(eids[qi], esc[qi]) if s > cut + 5e-4}
+        b = {int(i) for i, s in zip(eids[qi], esc[qi]) if s > cut + 2e-3 * abs(cut)}
         hit += len(b & set(ids[qi].cpu().tolist()))
         tot += len(b)
     assert hit / tot >= 0.999

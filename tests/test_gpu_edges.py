@@ -60,16 +60,47 @@ def test_bm25_tiny_and_ragged_corpora_vs_oracle(n_docs):
         assert np.array_equal(sc[qi].cpu().numpy(), esc), (n_docs, qi)
 
 
-def test_query_longer_than_the_kernel_limit_is_rejected():
+def test_queries_longer_than_the_kernel_term_table_are_scored_exactly():
+    """The reference has no query-length limit (bm25.py:149-156 loops over query.split()).  The kernels hold 128 terms per
+    CTA: longer queries are flagged (never truncated) and scored in chunks whose sums continue in query order - ids and
+    fp64 scores bit-equal to the oracle, for the top-k entry, the full-ranking entry and a batch mixing long and short queries."""
     from fusion_b200 import ops
-    from fusion_b200._lib import FusionB200Error
     from fusion_b200.index import LexicalIndex
-    (dptr, dtok), _ = synth.c3_lexical(300, 1, 40)
-    ix = LexicalIndex(dptr, dtok, 40, "bm25", 0.9, 0.4, tile_docs=256)
-    q_ptr = torch.tensor([0, 129], dtype=torch.int32).cuda()
-    q_term = torch.zeros(129, dtype=torch.int32).cuda()
-    with pytest.raises(FusionB200Error):
-        ops.sparse_topk(ix.view(), q_ptr, q_term, None, 10)
+    vocab = 60
+    (dptr, dtok), _ = synth.c3_lexical(700, 1, vocab)
+    ix = LexicalIndex(dptr, dtok, vocab, "bm25", 0.9, 0.4, tile_docs=256, tiled_min=8)
+    rng = np.random.default_rng(9)
+    lens = [300, 5, 129, 1, 128, 257]
+    toks = [rng.integers(0, vocab + 3, n) for n in lens]                 # ids >= vocab are out of vocabulary
+    q_ptr = np.zeros(len(lens) + 1, dtype=np.int32)
+    np.cumsum(lens, out=q_ptr[1:])
+    q_term = np.concatenate(toks).astype(np.int32)
+    q_term = np.where(q_term >= vocab, -1, q_term).astype(np.int32)
+    o = obm25.LexicalOracle(dptr, dtok, vocab, "bm25", 0.9, 0.4)
+    sc, ids = ops.sparse_topk(ix.view(), torch.from_numpy(q_ptr).cuda(), torch.from_numpy(q_term).cuda(), None, 50)
+    full = ops.sparse_scores(ix.view(), torch.from_numpy(q_ptr).cuda(), torch.from_numpy(q_term).cuda()).cpu().numpy()
+    for qi in range(len(lens)):
+        eids, esc = o.search_ids(q_term[q_ptr[qi]:q_ptr[qi + 1]], 50)
+        assert np.array_equal(ids[qi].cpu().numpy(), eids), qi
+        assert np.array_equal(sc[qi].cpu().numpy(), esc), qi
+        assert np.array_equal(np.sort(full[qi])[::-1][:50], esc), qi
+
+
+def test_splade_queries_longer_than_the_term_table():
+    from fusion_b200 import ops
+    from fusion_b200.index import SparseIndex, sparse_queries
+    from oracle import dense as odense
+    vocab, n_docs, k = 900, 3000, 40
+    dp, dt, dw = synth.splade_vectors(n_docs, vocab, 60, 8, 200, seed=311)
+    qp, qt, qw = synth.splade_vectors(4, vocab, 200, 150, 300, seed=312)         # 150 - 300 terms per query
+    qp2, qt2, qw2 = synth.splade_vectors(3, vocab, 12, 2, 40, seed=313)
+    qp = np.concatenate([qp, qp[-1] + qp2[1:]]); qt = np.concatenate([qt, qt2]); qw = np.concatenate([qw, qw2])
+    ix = SparseIndex(dp, dt, dw, vocab, "cos_sim", tile_docs=512, tiled_min=16, head_dim=64)
+    q_ptr, q_term, q_w = sparse_queries(qp, qt, qw, "cos_sim", ix.device)
+    sc, ids = ix.topk(q_ptr, q_term, q_w, k)
+    dd, qd = torch.from_numpy(synth.densify(dp, dt, dw, vocab)), torch.from_numpy(synth.densify(qp, qt, qw, vocab))
+    esc, eids = odense.topk_tensors(qd, dd, k, "cos_sim")
+    torch.testing.assert_close(sc.cpu(), esc, rtol=1e-5, atol=1e-5)
 
 
 @pytest.mark.parametrize("nq,n_docs,k", [(1, 5, 10), (3, 255, 255), (129, 257, 7)])
