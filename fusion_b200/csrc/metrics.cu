@@ -381,7 +381,7 @@ int fz_fuse_sweep(const int32_t* const* ids_h, const double* const* vals_h, cons
     int H = 64;
     while (H < 2 * total) H <<= 1;
     const size_t smem = (size_t)H * 8 + (size_t)H * n_sys * (values_are_f32 ? 4 : 8);
-    FZ_REQUIRE(smem <= 220 * 1024, "the union of the lists (%lld entries, %d systems) does not fit shared memory: sweep top-k "
+    FZ_REQUIRE(smem <= 212 * 1024, "the union of the lists (%lld entries, %d systems) does not fit shared memory: sweep top-k "
                "lists, not full rankings", total, n_sys);
     P.n_sys = n_sys;
     P.n_queries = n_queries;
@@ -396,8 +396,8 @@ int fz_fuse_sweep(const int32_t* const* ids_h, const double* const* vals_h, cons
     if (n_queries == 0) return FZ_OK;
     static bool attr = false;
     if (!attr) {
-        FZ_CUDA(cudaFuncSetAttribute(fuse_sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        FZ_CUDA(cudaFuncSetAttribute(fuse_sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        FZ_CUDA(cudaFuncSetAttribute(fuse_sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 212 * 1024));
+        FZ_CUDA(cudaFuncSetAttribute(fuse_sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 212 * 1024));
         attr = true;
     }
     ProfScope prof("fuse_sweep", stream);

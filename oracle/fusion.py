@@ -69,7 +69,7 @@ def transform(scores: list[float], transformation: str | None, distr=None):
 
 
 def fuse_query(ids_per_sys, scores_per_sys, method: str, normalization: str | None = None,
-               weights=None, distrs=None):
+               weights=None, distrs=None, promote_f64: bool = False):
     """One query.  ids_per_sys[s]: int array, scores_per_sys[s]: float64 array (rank order).
     -> (ids list, scores list) of the union, fused-score descending, ties by first insertion."""
     assert method in METHODS
@@ -82,7 +82,9 @@ def fuse_query(ids_per_sys, scores_per_sys, method: str, normalization: str | No
             vals = transform(sc, "reciprocal-rank")
         else:
             vals = transform(sc, normalization, None if distrs is None else distrs[s])
-            w = float(weights[s])          # python float: np.float32 * float stays fp32 (NEP 50)
+            # python float: np.float32 * float stays fp32 under NumPy >= 2 (NEP 50); NumPy 1.x (what the reference pins)
+            # promotes to float64 - identical to multiplying by an np.float64 scalar
+            w = np.float64(weights[s]) if promote_f64 else float(weights[s])
             vals = [v * w for v in vals]
         for i, v in zip(ids, vals):
             agg[i] = agg.get(i, 0.0) + v

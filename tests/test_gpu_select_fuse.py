@@ -71,6 +71,47 @@ def test_fuse_golden(golden_dir, method, norm):
         assert ids[qi, :n].tolist() == exp_ids[qi, :n].tolist(), (tag, qi)
 
 
+@pytest.mark.parametrize("norm", ["min-max", "z-score", "arctan", "percentile-rank"])
+def test_fuse_numpy1_promotion_golden(golden_dir, norm):
+    """FZ_FUSE_PROMOTE_F64 / Aggregator.fuse(numpy_promotion='legacy'): the reference's arithmetic under the NumPy 1.x it
+    pins (fp32 normalised scores weighted and summed in float64) - exact id sequence, scores to 1e-5 (fp32 normalisation)."""
+    from fusion_b200.retrievers.hybrid import Aggregator
+    ops = _ops()
+    g = np.load(os.path.join(golden_dir, "fusion_small.npz"))
+    leg = np.load(os.path.join(golden_dir, "fusion_legacy.npz"))
+    systems = [str(s) for s in g["systems"]]
+    lists = [(torch.from_numpy(g[f"in_ids_{s}"]).cuda(), torch.from_numpy(g[f"in_scores_{s}"]).cuda(), None) for s in systems]
+    ids, sc, lens = ops.fuse(lists, "nsf", norm, list(g["weights"]), [g[f"distr_{s}"] for s in systems], promote_f64=True)
+    exp_ids, exp_sc = leg[f"out_ids_{norm}"], leg[f"out_scores_{norm}"]
+    for qi in range(exp_ids.shape[0]):
+        n = int((exp_ids[qi] >= 0).sum())
+        assert int(lens[qi]) == n
+        assert ids[qi, :n].cpu().tolist() == exp_ids[qi, :n].tolist(), (norm, qi)
+        np.testing.assert_allclose(sc[qi, :n].cpu().numpy(), exp_sc[qi, :n], rtol=1e-5, atol=1e-5)
+    # the list-of-dict adapter: 'legacy' returns Python floats of the float64 sums, 'nep50' np.float32 like NumPy >= 2
+    ranked = {s: [[{"corpus_id": int(i), "score": float(v)} for i, v in zip(ri, rs)]
+                  for ri, rs in zip(g[f"in_ids_{s}"], g[f"in_scores_{s}"])] for s in systems}
+    w = dict(zip(systems, g["weights"].tolist()))
+    d = {s: g[f"distr_{s}"] for s in systems}
+    res = Aggregator.fuse(ranked, "nsf", norm, w, d, numpy_promotion="legacy")
+    assert [x["corpus_id"] for x in res[0]] == exp_ids[0, :len(res[0])].tolist() and isinstance(res[0][0]["score"], float)
+    res = Aggregator.fuse(ranked, "nsf", norm, w, d, numpy_promotion="nep50")
+    assert isinstance(res[0][0]["score"], np.float32)
+    assert Aggregator.fuse({s: [] for s in systems}, "nsf", norm, w, d) == []           # zero queries (hybrid.py returns [])
+
+
+def test_metrics_reject_more_gold_ids_than_the_kernel_holds():
+    """More than 256 distinct relevant docs for a query: an error, never a silently truncated recall / nDCG."""
+    from fusion_b200._lib import FusionB200Error
+    ops = _ops()
+    ids = torch.arange(1000, dtype=torch.int32).repeat(2, 1).cuda()
+    ok = ops.rank_metrics(ids, None, torch.tensor([0, 256, 300], dtype=torch.int32).cuda(),
+                          torch.arange(300, dtype=torch.int32).cuda())
+    assert float(ok[0]) > 0
+    with pytest.raises(FusionB200Error, match="256"):
+        ops.rank_metrics(ids, None, torch.tensor([0, 257, 300], dtype=torch.int32).cuda(), torch.arange(300, dtype=torch.int32).cuda())
+
+
 def _random_lists(rng, q, n_list, pool):
     lists = []
     for n in n_list:

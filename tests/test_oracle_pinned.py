@@ -142,3 +142,17 @@ def test_maxsim_oracle_matches_independent_padded_fixture(golden_dir):
     got = maxsim.maxsim_scores(torch.from_numpy(g["q"]), torch.from_numpy(g["tok_ptr"]), torch.from_numpy(g["tok_emb"]),
                                torch.from_numpy(g["cand"])).numpy()
     np.testing.assert_allclose(got, g["scores"], rtol=1e-6, atol=2e-6)
+
+
+@pytest.mark.parametrize("norm", ["min-max", "z-score", "arctan", "percentile-rank"])
+def test_fusion_oracle_numpy1_promotion(golden_dir, norm):
+    """NumPy 1.x promotion (fp32 normalised score * float weight -> float64, summed in float64): the oracle's
+    ``promote_f64`` mode against the verbatim reference run with np.float64 weights (oracle/make_golden_promotion.py)."""
+    g, leg = _load(golden_dir, "fusion_small.npz"), _load(golden_dir, "fusion_legacy.npz")
+    systems = [str(s) for s in g["systems"]]
+    for qi in range(leg[f"out_ids_{norm}"].shape[0]):
+        ids, sc = ofusion.fuse_query([g[f"in_ids_{s}"][qi] for s in systems], [g[f"in_scores_{s}"][qi] for s in systems], "nsf",
+                                     norm, list(g["weights"]), [g[f"distr_{s}"] for s in systems], promote_f64=True)
+        n = int((leg[f"out_ids_{norm}"][qi] >= 0).sum())
+        assert ids == leg[f"out_ids_{norm}"][qi, :n].tolist()
+        assert np.array_equal(np.array(sc, dtype=np.float64), leg[f"out_scores_{norm}"][qi, :n])
