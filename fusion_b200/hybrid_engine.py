@@ -31,6 +31,31 @@ class HybridQueries:
         return HybridQueries(**{f.name: (None if getattr(self, f.name) is None else
                                          getattr(self, f.name).to(device, non_blocking=non_blocking)) for f in fields(self)})
 
+    def to_sharded(self, device, group=None) -> tuple["HybridQueries", int]:
+        """Host (pinned) -> device with the corpus sharded over the ranks of ``group``: every rank needs EVERY query, but
+        uploading the whole batch on each rank sends it over PCIe G times.  The large row-major tensors (dense embeddings,
+        ColBERT query tokens: 97 % of the bytes) are uploaded 1/G per rank and all-gathered over NVLink; the small CSR
+        tensors are uploaded whole.  -> (device queries, bytes this rank copied host -> device)."""
+        world, rank = sharding._world(group)
+        if world == 1:
+            return self.to(device), self.nbytes()
+        out, h2d = {}, 0
+        for f in fields(self):
+            t = getattr(self, f.name)
+            if t is None:
+                out[f.name] = None
+            elif f.name in ("dense", "colbert"):
+                per = (t.shape[0] + world - 1) // world
+                lo, hi = min(t.shape[0], rank * per), min(t.shape[0], (rank + 1) * per)
+                part = torch.zeros((per,) + tuple(t.shape[1:]), dtype=t.dtype, device=device)
+                part[: hi - lo].copy_(t[lo:hi], non_blocking=True)
+                h2d += (hi - lo) * t[0].numel() * t.element_size()
+                out[f.name] = sharding.allgather_rows(part, group)[: t.shape[0]]
+            else:
+                out[f.name] = t.to(device, non_blocking=True)
+                h2d += t.numel() * t.element_size()
+        return HybridQueries(**out), h2d
+
     def pin(self) -> "HybridQueries":
         return HybridQueries(**{f.name: (None if getattr(self, f.name) is None else getattr(self, f.name).cpu().pin_memory())
                                 for f in fields(self)})
@@ -105,6 +130,9 @@ class HybridSearcher:
         # the kernel that follows the GEMM starts under its power cap, and SPLADE's is the one with the most headroom.
         # The returned dict keeps the system order bm25, splade, dpr, colbert (fusion breaks ties by first insertion,
         # hybrid.py:294-307).
+        # All three first-stage retrievers are LAUNCHED before any per-query status is read back: their fix-ups (overflow /
+        # fallback re-runs, rare) run after one host synchronisation per step instead of one per retriever; then the merges.
+        local, fixups = {}, []
         if self.dense is not None:
             def run_dense():
                 q32, q16 = self.dense.prepare_queries(q.dense)
@@ -115,17 +143,26 @@ class HybridSearcher:
                 return ops.dense_topk(q16, self.dense.d_bf16, q32 if exact else None, self.dense.d_f32 if exact else None,
                                       self.k, margin=self._dense_margin() if exact else 0.0, doc_base=self.dense.doc_base,
                                       tau_reduce=reduce, n_shards=self.world,
-                                      sched_docs=self._sync["dpr"].sched_docs if (reduce and "dpr" in self._sync) else None)
-            s, i = self._timed("dpr", run_dense)
-            out["dpr"] = self._timed("dpr_merge", lambda: self._merge(s, i))
+                                      sched_docs=self._sync["dpr"].sched_docs if (reduce and "dpr" in self._sync) else None,
+                                      defer=True)
+            s, i, fx = self._timed("dpr", run_dense)
+            local["dpr"] = (s, i)
+            fixups.append(fx)
         if self.sparse is not None:
-            s, i = self._timed("splade", lambda: self.sparse.topk(q.sp_ptr, q.sp_term, q.sp_weight, self.k,
-                                                                   sync=self._sync.get("splade")))
-            out["splade"] = self._timed("splade_merge", lambda: self._merge(s, i))
+            s, i, fx = self._timed("splade", lambda: self.sparse.topk(q.sp_ptr, q.sp_term, q.sp_weight, self.k,
+                                                                       sync=self._sync.get("splade"), defer=True))
+            local["splade"] = (s, i)
+            fixups.append(fx)
         if self.lexical is not None:
-            s, i = self._timed("bm25", lambda: ops.sparse_topk(self.lexical.view(), q.lex_ptr, q.lex_term, None, self.k,
-                                                                self.lexical.doc_base, sync=self._sync.get("bm25")))
-            out["bm25"] = self._timed("bm25_merge", lambda: self._merge(s, i))
+            s, i, fx = self._timed("bm25", lambda: ops.sparse_topk(self.lexical.view(), q.lex_ptr, q.lex_term, None, self.k,
+                                                                    self.lexical.doc_base, sync=self._sync.get("bm25"), defer=True))
+            local["bm25"] = (s, i)
+            fixups.append(fx)
+        self._timed("status_fixups", lambda: [fx() for fx in fixups])
+        for name in ("dpr", "splade", "bm25"):
+            if name in local:
+                s, i = local[name]
+                out[name] = self._timed(f"{name}_merge", lambda: self._merge(s, i))
         if self.tokens is not None:
             out["colbert"] = self._timed("colbert", lambda: self._colbert(q, out))
         return {name: out[name] for name in ("bm25", "splade", "dpr", "colbert") if name in out}
@@ -173,7 +210,8 @@ class HybridSearcher:
     def search_host(self, q_host: HybridQueries, out_ids: torch.Tensor, out_scores: torch.Tensor, out_k: int | None = None):
         """End-to-end call with HOST buffers: pinned inputs -> device, search, fused top-k -> pinned outputs."""
         dev = torch.device("cuda", torch.cuda.current_device())
-        ids, scores, lens = self.search(q_host.to(dev), out_k)
+        q_dev, self.last_h2d_bytes = q_host.to_sharded(dev, self.group)
+        ids, scores, lens = self.search(q_dev, out_k)
         out_ids[: ids.shape[0]].copy_(ids, non_blocking=True)
         out_scores[: scores.shape[0]].copy_(scores, non_blocking=True)
         torch.cuda.current_stream().synchronize()

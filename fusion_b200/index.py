@@ -355,11 +355,12 @@ class SparseIndex:
             self._view = self._general_view(self.n_docs)
         return self._view
 
-    def topk(self, q_ptr, q_term, q_weight, k: int, cap: int = ops.DEFAULT_CAP, sync: "ops.ShardSync | None" = None):
+    def topk(self, q_ptr, q_term, q_weight, k: int, cap: int = ops.DEFAULT_CAP, sync: "ops.ShardSync | None" = None,
+             defer: bool = False):
         """Top-k of one query batch: the head/tail pipeline when the index has one, else the general inverted index."""
         if self.head is not None:
-            return ops.splade_topk(self, q_ptr, q_term, q_weight, k, self.doc_base, cap=cap, sync=sync)
-        return ops.sparse_topk(self.view(), q_ptr, q_term, q_weight, k, self.doc_base, cap=cap, sync=sync)
+            return ops.splade_topk(self, q_ptr, q_term, q_weight, k, self.doc_base, cap=cap, sync=sync, defer=defer)
+        return ops.sparse_topk(self.view(), q_ptr, q_term, q_weight, k, self.doc_base, cap=cap, sync=sync, defer=defer)
 
     def nbytes(self) -> int:
         b = self.doc_ptr.numel() * 8 + self.doc_post.numel() * 4

@@ -375,7 +375,7 @@ def _subset_queries(q_ptr, q_term, q_weight, sel):
 
 
 def sparse_topk(pv: PostingsView, q_ptr, q_term, q_weight, k: int, doc_base: int = 0, cap: int = DEFAULT_CAP,
-                growth: int = DEFAULT_GROWTH, sync: ShardSync | None = None):
+                growth: int = DEFAULT_GROWTH, sync: ShardSync | None = None, defer: bool = False):
     """Top-k of sum_t w_qt * val[t, d] over an inverted index -> (scores [Q,k], ids [Q,k] int32).
 
     Order: score desc, ties by lower doc id; docs that match nothing score 0 and fill up in doc-id order; negative
@@ -385,7 +385,11 @@ def sparse_topk(pv: PostingsView, q_ptr, q_term, q_weight, k: int, doc_base: int
     ``sync`` (corpus sharded over several GPUs): the shards agree on a per-query score floor between rounds, so each
     keeps only what can still reach the GLOBAL top-k; the local list may then hold fewer than k real entries (padded
     with (-inf, -1)), the merge of the shards' lists is unchanged.  The rare re-runs below never use it: they are
-    decided per rank and must not issue collectives."""
+    decided per rank and must not issue collectives.
+
+    ``defer``: return ``(scores, ids, fixup)`` without reading the per-query status back; ``fixup()`` reads it (the one
+    host synchronisation of the call) and repairs the flagged rows in place.  A pipeline of several retrievers launches
+    them all first and then runs the fix-ups: one pipeline drain per step instead of one per retriever."""
     q_ptr = _req(q_ptr, torch.int32, "q_ptr")
     q_term = _req(q_term, torch.int32, "q_term")
     if q_weight is not None:
@@ -393,6 +397,16 @@ def sparse_topk(pv: PostingsView, q_ptr, q_term, q_weight, k: int, doc_base: int
     k_eff = min(k, pv.n_docs)
     cap = max(cap, 2 * k_eff)
     out_s, out_i, status = _sparse_topk_once(pv, q_ptr, q_term, q_weight, k_eff, doc_base, cap, growth, +1, sync, k)
+
+    def fixup():
+        _sparse_topk_fixup(pv, q_ptr, q_term, q_weight, k_eff, doc_base, cap, out_s, out_i, status)
+    if defer:
+        return out_s, out_i, fixup
+    fixup()
+    return out_s, out_i
+
+
+def _sparse_topk_fixup(pv, q_ptr, q_term, q_weight, k_eff, doc_base, cap, out_s, out_i, status):
     st = status.cpu()
     too_long = (st & FZ_STATUS_TOO_LONG) != 0
     if bool(too_long.any()):        # rare: more terms than a CTA holds - every document scored in term chunks, rows ranked
@@ -421,7 +435,6 @@ def sparse_topk(pv: PostingsView, q_ptr, q_term, q_weight, k: int, doc_base: int
             take = k_eff - have
             out_s[qi, have:] = s2[j, :take]
             out_i[qi, have:] = i2[j, :take]
-    return out_s, out_i
 
 
 @dataclass
@@ -454,7 +467,8 @@ SPLADE_MAX_ROUND_DOCS = 1 << 21    # bounds the code buffer: n_queries * max_rou
 
 
 def splade_topk(index, q_ptr, q_term, q_weight, k: int, doc_base: int = 0, cap: int = DEFAULT_CAP,
-                growth: int = SPLADE_GROWTH, sync: ShardSync | None = None, max_round_docs: int = SPLADE_MAX_ROUND_DOCS):
+                growth: int = SPLADE_GROWTH, sync: ShardSync | None = None, max_round_docs: int = SPLADE_MAX_ROUND_DOCS,
+                defer: bool = False):
     """SPLADE top-k through ``fz_splade_topk``: head terms on the tensor cores, a 4-bit upper bound of the tail sum per
     (query, doc), exact fp32 rescoring of the survivors.  ``index``: a ``fusion_b200.index.SparseIndex`` with a head/tail
     split.  Same result contract as :func:`sparse_topk` (scores exact fp32 sparse dot products, score desc, ties by lower
@@ -474,7 +488,7 @@ def splade_topk(index, q_ptr, q_term, q_weight, k: int, doc_base: int = 0, cap: 
     out_i = torch.empty((nq, k_eff), dtype=torch.int32, device=dev)
     status = torch.empty((nq,), dtype=torch.int32, device=dev)
     if nq == 0:
-        return out_s, out_i
+        return (out_s, out_i, lambda: None) if defer else (out_s, out_i)
     round_docs = max(256, min(int(max_round_docs), (hv.n_docs + 255) // 256 * 256))
     ws = _ws(lib.fz_splade_topk_workspace_bytes(nq, k_eff, cap, hv.head_dim, round_docs), dev)
     sc = _SyncCall(sync, nq, torch.float32, dev, k)
@@ -484,13 +498,17 @@ def splade_topk(index, q_ptr, q_term, q_weight, k: int, doc_base: int = 0, cap: 
                             growth, _ptr(out_s), _ptr(out_i), _ptr(status), _ptr(ws), ws.numel(), sc.ref(), _stream(out_s))
     sc.reraise()
     check(rc, "fz_splade_topk")
-    bad = (status & (FZ_STATUS_OVERFLOW | FZ_STATUS_FALLBACK)) != 0
-    bad[_long_queries(q_ptr)] = True       # more terms than the kernels' per-query tables: the general path scores them in chunks
-    if bool(bad.any()):
-        sel = torch.nonzero(bad).flatten()
-        p2, t2, w2 = _subset_queries(q_ptr, q_term, q_weight, sel)
-        s2, i2 = sparse_topk(index.view(), p2, t2, w2, k_eff, doc_base, cap=cap)
-        out_s[sel], out_i[sel] = s2, i2
+    def fixup():
+        bad = (status & (FZ_STATUS_OVERFLOW | FZ_STATUS_FALLBACK)) != 0
+        bad[_long_queries(q_ptr)] = True   # more terms than the kernels' per-query tables: the general path scores them in chunks
+        if bool(bad.any()):
+            sel = torch.nonzero(bad).flatten()
+            p2, t2, w2 = _subset_queries(q_ptr, q_term, q_weight, sel)
+            s2, i2 = sparse_topk(index.view(), p2, t2, w2, k_eff, doc_base, cap=cap)
+            out_s[sel], out_i[sel] = s2, i2
+    if defer:
+        return out_s, out_i, fixup
+    fixup()
     return out_s, out_i
 
 
@@ -558,7 +576,7 @@ def normalize_rows(x: torch.Tensor, normalize: bool = True, want_f32: bool = Tru
 
 def dense_topk(q_bf16, d_bf16, q_f32, d_f32, k: int, margin: float = 0.0, doc_base: int = 0,
                cap: int = DEFAULT_CAP, growth: int = DEFAULT_GROWTH, tau_reduce=None, n_shards: int = 1,
-               sched_docs: int | None = None):
+               sched_docs: int | None = None, defer: bool = False):
     """Exhaustive inner-product top-k (tcgen05 GEMM with the threshold filter in its epilogue).
 
     q_bf16 [Q, d], d_bf16 [N, d] are the tensor-core operands; with q_f32 / d_f32 the survivors within ``margin`` of
@@ -566,7 +584,9 @@ def dense_topk(q_bf16, d_bf16, q_f32, d_f32, k: int, margin: float = 0.0, doc_ba
     ``tau_reduce`` (exact mode, corpus sharded over ``n_shards``): a callable that takes the element-wise MINIMUM of a [Q]
     tensor over the shards (one all-reduce).  Every shard reports its ceil(k / n_shards)-th best score; the minimum
     bounds the global k-th score from below, and candidates under it (minus the margin) are not rescored.  With
-    ``sched_docs`` (largest shard size) the same exchange also runs between the filter rounds (``ShardSync``)."""
+    ``sched_docs`` (largest shard size) the same exchange also runs between the filter rounds (``ShardSync``).
+    ``defer``: return ``(scores, ids, fixup)``; the overflow check (a host synchronisation) and the rare re-run happen in
+    ``fixup()`` - the first pass is finished optimistically, a re-run never issues a collective."""
     lib = _lib.load()
     q_bf16 = _req(q_bf16, torch.bfloat16, "q_bf16")
     d_bf16 = _req(d_bf16, torch.bfloat16, "d_bf16")
@@ -605,19 +625,29 @@ def dense_topk(q_bf16, d_bf16, q_f32, d_f32, k: int, margin: float = 0.0, doc_ba
     # survivors of the plain filter, so the doc ranges may only grow 3x per round instead of 4x.
     if margin > 0:
         growth = min(growth, 3)
+    def finish(floor):
+        check(lib.fz_dense_topk_finish(_ptr(q_f32), _ptr(d_f32), _ptr(floor), nq, dim, k_eff, doc_base, cap, _ptr(out_s),
+                                       _ptr(out_i), _ptr(status), _ptr(ws), ws.numel(), _stream(out_s)),
+              "fz_dense_topk_finish")
+
     run(growth, first=True)
-    if bool(((status & FZ_STATUS_OVERFLOW) != 0).any()):
+    if staged:
+        finish(tau_reduce(tau))             # every shard calls the collective exactly once, whatever happens below
+
+    def fixup():
+        if not bool(((status & FZ_STATUS_OVERFLOW) != 0).any()):
+            return
         if margin > 0:
             run(2)
             if bool(((status & FZ_STATUS_OVERFLOW) != 0).any()):
                 raise FusionB200Error("dense top-k candidate buffer overflowed: lower `margin` or raise `cap`")
         else:
             run(1)      # conservative rounds never overflow when margin == 0
-    if staged:
-        floor = tau_reduce(tau)
-        check(lib.fz_dense_topk_finish(_ptr(q_f32), _ptr(d_f32), _ptr(floor), nq, dim, k_eff, doc_base, cap, _ptr(out_s),
-                                       _ptr(out_i), _ptr(status), _ptr(ws), ws.numel(), _stream(out_s)),
-              "fz_dense_topk_finish")
+        if staged:
+            finish(None)                    # decided per rank: no floor, no collective
+    if defer:
+        return out_s, out_i, fixup
+    fixup()
     return out_s, out_i
 
 

@@ -169,16 +169,45 @@ class Ranker:
                 for ri, rs in zip(ids.cpu().tolist(), scores.cpu().tolist())]
 
     @staticmethod
-    def maxsim_search_tensors(q_tok: torch.Tensor, store: TokenStore, top_k: int, cand_ids: torch.Tensor | None = None):
-        """MaxSim-score candidates (all documents when ``cand_ids`` is None) and rank them."""
+    def maxsim_search_tensors(q_tok: torch.Tensor, store: TokenStore, top_k: int, cand_ids: torch.Tensor | None = None,
+                              group=None, chunk_pairs: int = 1 << 24):
+        """MaxSim-score candidates and rank them.  ``cand_ids`` None = EXHAUSTIVE search (``CustomSearcher.search_all`` without
+        PLAID candidate generation, colbert_ir.py:245-255): every passage of the store is scored, in chunks of passages so
+        that the [Q, chunk] score block stays bounded, and the chunks' top-k lists are merged on the device.  With a process
+        ``group`` the store is this rank's shard of the collection: the shards' lists are merged over NCCL and every rank
+        gets the global top-k of all queries."""
+        from .. import sharding
         q16 = q_tok.to(torch.bfloat16).contiguous()
         nq = q16.shape[0]
-        if cand_ids is None:
-            cand_ids = (torch.arange(store.n_docs, dtype=torch.int32, device=q16.device) + store.doc_base).expand(nq, -1).contiguous()
-        sc = ops.maxsim(q16, store.tok_ptr, None, cand_ids, store.doc_base, packed=store.packed())
-        k = min(top_k, cand_ids.shape[1])
-        order_s, order_i = ops.rank_rows(sc, k, 0)
-        return order_s, torch.gather(cand_ids, 1, order_i.long())
+        if cand_ids is not None:
+            sc = ops.maxsim(q16, store.tok_ptr, None, cand_ids, store.doc_base, packed=store.packed())
+            k = min(top_k, cand_ids.shape[1])
+            order_s, order_i = ops.rank_rows(sc, k, 0)
+            return order_s, torch.gather(cand_ids, 1, order_i.long())
+        n = store.n_docs
+        world, _ = sharding._world(group)
+        n_total = n if world == 1 else sharding.allreduce_max_ints([n], q16.device, group)[0] * world    # (bound on the global size)
+        k = min(top_k, n_total)
+        step = max(1, chunk_pairs // max(nq, 1))
+        parts_s, parts_i = [], []
+        for lo in range(0, n, step):
+            hi = min(n, lo + step)
+            ids = (torch.arange(lo, hi, dtype=torch.int32, device=q16.device) + store.doc_base).expand(nq, -1).contiguous()
+            sc = ops.maxsim(q16, store.tok_ptr, None, ids, store.doc_base, packed=store.packed())
+            kk = min(k, hi - lo)
+            s2, i2 = ops.rank_rows(sc, kk, store.doc_base + lo)
+            if kk < k:      # pad to a common width for the merge
+                s2 = torch.cat([s2, torch.full((nq, k - kk), float("-inf"), device=s2.device)], 1)
+                i2 = torch.cat([i2, torch.full((nq, k - kk), -1, dtype=torch.int32, device=i2.device)], 1)
+            parts_s.append(s2)
+            parts_i.append(i2)
+        if not parts_s:
+            parts_s = [torch.full((nq, k), float("-inf"), device=q16.device)]
+            parts_i = [torch.full((nq, k), -1, dtype=torch.int32, device=q16.device)]
+        sc, ids = (parts_s[0], parts_i[0]) if len(parts_s) == 1 else ops.merge_topk(torch.stack(parts_s), torch.stack(parts_i), k)
+        if world > 1:
+            sc, ids = sharding.gather_merge_topk(sc.contiguous(), ids.contiguous(), k, group)
+        return sc, ids
 
 
 def weight_grid(systems: list[str], step: float = 0.05) -> list[dict[str, float]]:

@@ -16,15 +16,19 @@ from ..retrievers.hybrid import Ranker
 
 
 class CustomSearcher:
-    def __init__(self, store: TokenStore, encoder=None):
+    """``search_all`` without a PLAID index: exhaustive MaxSim over the token store (this rank's shard of the collection when
+    a process ``group`` is given; the shards' top-k lists are then merged over NCCL), or rescoring of given candidates."""
+
+    def __init__(self, store: TokenStore, encoder=None, group=None):
         self.store = store
         self.encoder = encoder
+        self.group = group
 
     def encode(self, queries: list[str]) -> torch.Tensor:
         return self.encoder.encode_queries(queries)
 
     def search_all_tensors(self, q_tok: torch.Tensor, k: int, cand_ids: torch.Tensor | None = None):
-        return Ranker.maxsim_search_tensors(q_tok.cuda(), self.store, k, cand_ids)
+        return Ranker.maxsim_search_tensors(q_tok.cuda(), self.store, k, cand_ids, group=self.group)
 
     def search_all(self, queries: dict, k: int = 10, cand_ids: torch.Tensor | None = None):
         """queries: {qid: text}.  -> {qid: [(pid, rank, score), ...]} like ``Ranking.todict()`` (colbert_ir.py:245-255)."""

@@ -84,6 +84,14 @@ def main():
     agree = float((fi[:, :50] == si[:, :50]).float().mean())
     print(f"rank {rank} fused top-50 ids equal {agree:.4f}", flush=True)
     ok &= agree > 0.98
+    # exhaustive ColBERT search_all over the SHARDED token store: shards' top-k merged over NCCL == one store
+    from fusion_b200.retrievers.hybrid import Ranker
+    qs = qtok_c[:16]
+    es, ei = Ranker.maxsim_search_tensors(qs, shard.tokens, 50, group=dist.group.WORLD, chunk_pairs=16 * 3000)
+    fs, fi = Ranker.maxsim_search_tensors(qs, full.tokens, 50, chunk_pairs=16 * 7000)
+    good = torch.allclose(es, fs, rtol=1e-5, atol=1e-4) and float((ei == fi).float().mean()) > 0.995
+    print(f"rank {rank} exhaustive colbert: {'OK' if good else 'MISMATCH'} ids equal {float((ei == fi).float().mean()):.4f}", flush=True)
+    ok &= good
     t = torch.tensor([0 if ok else 1], device=dev)
     dist.all_reduce(t)
     if rank == 0:

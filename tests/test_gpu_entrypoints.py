@@ -279,7 +279,13 @@ def test_ranker_multi_vector_search_and_custom_searcher(golden_dir):
         order = np.argsort(-want, kind="stable")[:10]
         assert [x["corpus_id"] for x in res[qi]] == [pids[keep[j]] for j in order]
         np.testing.assert_allclose([x["score"] for x in res[qi]], want[order], rtol=1e-5, atol=1e-4)
+    # the exhaustive search walks the store in chunks of passages and merges the chunks' lists: same result
     ptr, emb = enc.encode_docs([f"d{d}" for d in keep])
+    st = TokenStore(ptr.cuda(), emb.cuda().to(torch.bfloat16))
+    q16 = torch.from_numpy(g["q"]).cuda()
+    s1, i1 = Ranker.maxsim_search_tensors(q16, st, 10)
+    s2, i2 = Ranker.maxsim_search_tensors(q16, st, 10, chunk_pairs=nq * 17)
+    assert torch.equal(i1, i2) and torch.equal(s1, s2)
     searcher = CustomSearcher(TokenStore(ptr.cuda(), emb.cuda().to(torch.bfloat16)), encoder=enc)
     ranking = searcher.search_all({f"qid{i}": f"q{i}" for i in range(nq)}, k=5)
     assert list(ranking) == [f"qid{i}" for i in range(nq)]

@@ -110,6 +110,16 @@ def _worker(rank, world, port, n_docs, nq, k, ret):
         t = torch.tensor([float(rank), 5.0 - rank, float("-inf") if rank == 0 else 3.0], dtype=torch.float64)
         assert sharding.allreduce_min(t).tolist() == [0.0, 5.0 - (world - 1), float("-inf")]
         _floor_protocol(rank, world, scores, k)
+        # sharded query upload: every rank copies 1/G of the large query tensors and all-gathers them (HybridQueries.to_sharded)
+        from fusion_b200.hybrid_engine import HybridQueries
+        g = torch.Generator().manual_seed(5)
+        hq = HybridQueries(lex_ptr=torch.arange(nq + 1, dtype=torch.int32), lex_term=torch.arange(nq, dtype=torch.int32),
+                           dense=torch.randn((nq, 8), generator=g), colbert=torch.randn((nq, 3, 4), generator=g).bfloat16())
+        dq, h2d = hq.to_sharded("cpu")
+        assert torch.equal(dq.dense, hq.dense) and torch.equal(dq.colbert, hq.colbert) and torch.equal(dq.lex_term, hq.lex_term)
+        per = -(-nq // world)
+        rows = max(0, min(nq, (rank + 1) * per) - min(nq, rank * per))
+        assert h2d == (nq + 1) * 4 + nq * 4 + rows * (8 * 4 + 12 * 2)
         ret[rank] = True
     finally:
         dist.destroy_process_group()
