@@ -212,7 +212,8 @@ class LexicalIndex:
     @classmethod
     def from_postings(cls, term_ptr, post_doc, post_tf, doc_len, vocab_size: int, variant: str = "bm25", k1: float = 0.9,
                       b: float = 0.4, device="cuda", doc_base: int = 0, tile_docs: int = LEX_TILE_DOCS,
-                      tiled_min: int | None = None, dense_frac: float = DENSE_FRAC):
+                      tiled_min: int | None = None, dense_frac: float = DENSE_FRAC, global_n_docs: int | None = None,
+                      global_df=None, avgdl: float | None = None):
         """Rebuild the index from saved term-major CSR arrays (``BM25.load_indexes``): no tokenisation, no sort."""
         if variant not in VARIANTS:
             raise FusionB200Error(f"unknown lexical variant {variant!r}")
@@ -226,13 +227,32 @@ class LexicalIndex:
         self.post_tf = torch.as_tensor(np.asarray(post_tf), dtype=torch.int32, device=self.device)
         self.doc_len = torch.as_tensor(np.asarray(doc_len), dtype=torch.int32, device=self.device)
         self.n_docs = self.doc_len.numel()
-        self.global_n_docs = self.n_docs
-        self.df = (self.term_ptr[1:] - self.term_ptr[:-1]).cpu().numpy()
+        # corpus-global statistics of a sharded index are stored with the shard (N, df, avgdl)
+        self.global_n_docs = int(global_n_docs) if global_n_docs is not None else self.n_docs
+        self.df = np.asarray(global_df) if global_df is not None else (self.term_ptr[1:] - self.term_ptr[:-1]).cpu().numpy()
         sum_dl = int(self.doc_len.long().sum())
-        self.avgdl = float(Fraction(sum_dl, self.global_n_docs)) if self.global_n_docs else 0.0
+        self.avgdl = float(avgdl) if avgdl is not None else (float(Fraction(sum_dl, self.global_n_docs)) if self.global_n_docs else 0.0)
         self.idf = torch.from_numpy(idf_table(self.df, self.global_n_docs, variant)).to(self.device)
         self._dl_values = torch.unique(self.doc_len).cpu().numpy().astype(np.float64)
         self.update_params(k1, b)
+        return self
+
+    def save(self, path: str) -> None:
+        """Persist the shard's term-major CSR and statistics (``.npz``); ``load`` rebuilds the device index from it without
+        tokenising or sorting.  (The reference pickles its dicts, bm25.py:117-126, and has no loader.)"""
+        np.savez(path, term_ptr=self.term_ptr.cpu().numpy(), post_doc=self.post_doc.cpu().numpy(),
+                 post_tf=self.post_tf.cpu().numpy(), doc_len=self.doc_len.cpu().numpy(), df=np.asarray(self.df),
+                 meta=np.array([self.vocab_size, self.doc_base, self.global_n_docs, self.tile_docs], dtype=np.int64),
+                 params=np.array([self.k1, self.b, self.avgdl, self.dense_frac], dtype=np.float64), variant=np.array(self.variant))
+
+    @classmethod
+    def load(cls, path: str, device="cuda", tiled_min: int | None = None):
+        g = np.load(path if str(path).endswith(".npz") else str(path) + ".npz", allow_pickle=False)
+        vocab, doc_base, n_global, tile_docs = (int(x) for x in g["meta"])
+        k1, b, avgdl, dense_frac = (float(x) for x in g["params"])
+        self = cls.from_postings(g["term_ptr"], g["post_doc"], g["post_tf"], g["doc_len"], vocab, str(g["variant"]), k1, b,
+                                 device=device, doc_base=doc_base, tile_docs=tile_docs, tiled_min=tiled_min, dense_frac=dense_frac,
+                                 global_n_docs=n_global, global_df=g["df"], avgdl=avgdl)
         return self
 
     def update_params(self, k1: float, b: float) -> None:
@@ -338,6 +358,27 @@ class SparseIndex:
         self.head = ops.SpladeHeadView(head, term_head, term_max, self.doc_ptr, self.doc_post, tail, head_dim, v, n,
                                        unit_rows=self.similarity == "cos_sim")
 
+    def save(self, path: str) -> None:
+        """Persist the shard as its doc-major CSR (normalised weights) + parameters; ``load`` rebuilds the device forms."""
+        hd = self.head.head_dim if self.head is not None else 0
+        boot = self.head.boot.n_docs if (self.head is not None and self.head.boot is not None) else 0
+        np.savez(path, doc_ptr=self.doc_ptr.cpu().numpy(), doc_term=self.doc_post[:, 0].cpu().numpy(),
+                 doc_weight=self.doc_post[:, 1].contiguous().view(torch.float32).cpu().numpy(),
+                 meta=np.array([self.vocab_size, self.doc_base, self.tile_docs, hd, boot], dtype=np.int64),
+                 similarity=np.array(self.similarity), dense_frac=np.array(self.dense_frac))
+
+    @classmethod
+    def load(cls, path: str, device="cuda"):
+        g = np.load(path if str(path).endswith(".npz") else str(path) + ".npz", allow_pickle=False)
+        vocab, doc_base, tile_docs, hd, boot = (int(x) for x in g["meta"])
+        # the stored weights are already normalised: build with "dot" (no renormalisation), then restore the similarity
+        self = cls(g["doc_ptr"], g["doc_term"], g["doc_weight"], vocab, "dot", device=device, doc_base=doc_base, tile_docs=tile_docs,
+                   dense_frac=float(g["dense_frac"]), head_dim=hd, boot_docs=boot)
+        self.similarity = str(g["similarity"])
+        if self.head is not None:
+            self.head.unit_rows = self.similarity == "cos_sim"
+        return self
+
     def _general_view(self, n_docs: int) -> ops.PostingsView:
         """The three-form inverted index over all terms of the first ``n_docs`` docs."""
         nnz = int(self.doc_ptr[n_docs])
@@ -404,6 +445,21 @@ class DenseIndex:
     def n_docs(self) -> int:
         return self.d_bf16.shape[0]
 
+    def save(self, path: str) -> None:
+        """Persist the (normalised) fp32 rows, or the bf16 rows of a throughput-mode index, + parameters."""
+        rows = self.d_f32 if self.d_f32 is not None else self.d_bf16.view(torch.int16)
+        np.savez(path, rows=rows.cpu().numpy(), is_f32=np.array(self.d_f32 is not None), similarity=np.array(self.similarity),
+                 doc_base=np.array(self.doc_base))
+
+    @classmethod
+    def load(cls, path: str, device="cuda"):
+        g = np.load(path if str(path).endswith(".npz") else str(path) + ".npz", allow_pickle=False)
+        rows = torch.from_numpy(g["rows"]).to(device)
+        if bool(g["is_f32"]):
+            d32, d16 = ops.normalize_rows(rows, normalize=False)       # stored rows are already normalised: convert only
+            return cls(d32, d16, str(g["similarity"]), int(g["doc_base"]))
+        return cls(None, rows.view(torch.bfloat16), str(g["similarity"]), int(g["doc_base"]))
+
     def prepare_queries(self, q: torch.Tensor):
         return ops.normalize_rows(q, normalize=self.similarity == "cos_sim")
 
@@ -424,6 +480,19 @@ class TokenStore:
     @property
     def n_tokens(self) -> int:
         return int(self.tok_ptr[-1])
+
+    def save(self, path: str) -> None:
+        """Persist the per-passage offsets and the bf16 token rows (the packed image is rebuilt on load)."""
+        if self.tok_emb is None:
+            raise FusionB200Error("the plain token matrix was dropped (packed(drop_plain=True)): nothing to save")
+        np.savez(path, tok_ptr=self.tok_ptr.cpu().numpy(), tok_emb=self.tok_emb.view(torch.int16).cpu().numpy(),
+                 doc_base=np.array(self.doc_base))
+
+    @classmethod
+    def load(cls, path: str, device="cuda"):
+        g = np.load(path if str(path).endswith(".npz") else str(path) + ".npz", allow_pickle=False)
+        return cls(torch.from_numpy(g["tok_ptr"]).to(device), torch.from_numpy(g["tok_emb"]).to(device).view(torch.bfloat16),
+                   int(g["doc_base"]))
 
     def packed(self, drop_plain: bool = False):
         if self._packed is None:
