@@ -174,8 +174,8 @@ class Ranker:
         """MaxSim-score candidates and rank them.  ``cand_ids`` None = EXHAUSTIVE search (``CustomSearcher.search_all`` without
         PLAID candidate generation, colbert_ir.py:245-255): every passage of the store is scored, in chunks of passages so
         that the [Q, chunk] score block stays bounded, and the chunks' top-k lists are merged on the device.  With a process
-        ``group`` the store is this rank's shard of the collection: the shards' lists are merged over NCCL and every rank
-        gets the global top-k of all queries."""
+        ``group`` (None = the default group when torch.distributed is initialised, False = never) the store is this rank's shard
+        of the collection: the shards' lists are merged over NCCL and every rank gets the global top-k of all queries."""
         from .. import sharding
         q16 = q_tok.to(torch.bfloat16).contiguous()
         nq = q16.shape[0]
@@ -185,7 +185,7 @@ class Ranker:
             order_s, order_i = ops.rank_rows(sc, k, 0)
             return order_s, torch.gather(cand_ids, 1, order_i.long())
         n = store.n_docs
-        world, _ = sharding._world(group)
+        world = 1 if group is False else sharding._world(group)[0]       # group=False: this store is the whole collection
         n_total = n if world == 1 else sharding.allreduce_max_ints([n], q16.device, group)[0] * world    # (bound on the global size)
         k = min(top_k, n_total)
         step = max(1, chunk_pairs // max(nq, 1))
