@@ -10,9 +10,9 @@ python scripts/bench_summary.py gpurun_out/plain.json
 timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1; echo launches $?
 NCU="ncu --set full --clock-control none --import-source on --profile-from-start off"
 timeout 600 $NCU -k regex:tail_codes_kernel -s 4 -c 1 -f -o gpurun_out/prof_r02_tail_codes $CMD > gpurun_out/ncu_tail.log 2>&1; echo tail $?
-timeout 600 $NCU -k "regex:filter_gemm_kernel<\(bool\)1>|filter_gemm_kernel<true>" -s 4 -c 1 -f -o gpurun_out/prof_r02_head_gemm $CMD > gpurun_out/ncu_head.log 2>&1; echo head $?
+timeout 600 $NCU -k regex:filter_gemm_kernel -s 12 -c 1 -f -o gpurun_out/prof_r02_head_gemm $CMD > gpurun_out/ncu_head.log 2>&1; echo head $?
 timeout 600 $NCU -k regex:sparse_rescore_kernel -s 5 -c 1 -f -o gpurun_out/prof_r02_rescore $CMD > gpurun_out/ncu_rescore.log 2>&1; echo rescore $?
-timeout 600 $NCU -k "regex:sparse_tile_kernel<double" -s 5 -c 1 -f -o gpurun_out/prof_r02_sparse_f64 $CMD > gpurun_out/ncu_f64.log 2>&1; echo f64 $?
-timeout 600 $NCU -k "regex:filter_gemm_kernel<\(bool\)0>|filter_gemm_kernel<false>" -s 6 -c 1 -f -o gpurun_out/prof_r02_dense $CMD > gpurun_out/ncu_dense.log 2>&1; echo dense $?
+timeout 600 $NCU -k "regex:^sparse_tile_kernel$" -s 5 -c 1 -f -o gpurun_out/prof_r02_sparse_f64 $CMD > gpurun_out/ncu_f64.log 2>&1; echo f64 $?
+timeout 600 $NCU -k regex:filter_gemm_kernel -s 6 -c 1 -f -o gpurun_out/prof_r02_dense $CMD > gpurun_out/ncu_dense.log 2>&1; echo dense $?
 timeout 600 $NCU -k regex:maxsim_kernel -c 1 -f -o gpurun_out/prof_r02_maxsim $CMD > gpurun_out/ncu_maxsim.log 2>&1; echo maxsim $?
 ls -la gpurun_out/prof_r02_*.ncu-rep

@@ -12,6 +12,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "profiles")
 SRC = os.path.join(ROOT, "gpurun_out")
 KEYS = [
+    "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum",
+    "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_registers", "launch__occupancy_limit_warps",
     "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
     "lts__t_bytes.sum", "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
     "l1tex__throughput.avg.pct_of_peak_sustained_active", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
@@ -62,8 +65,12 @@ def launches(rnd):
 
 def kernels(rnd):
     traffic = {}
-    for tag, rep in [("sparse_tile_f64", "prof_sparse_f64"), ("sparse_tile_f32", "prof_sparse_f32"),
-                     ("dense_filter_gemm", "prof_dense"), ("maxsim", "prof_maxsim")]:
+    reps = {"r01": [("sparse_tile_f64", "prof_sparse_f64"), ("sparse_tile_f32", "prof_sparse_f32"),
+                    ("dense_filter_gemm", "prof_dense"), ("maxsim", "prof_maxsim")],
+            "r02": [("sparse_tile_f64", "prof_r02_sparse_f64"), ("dense_filter_gemm", "prof_r02_dense"), ("maxsim", "prof_r02_maxsim"),
+                    ("splade_head_gemm", "prof_r02_head_gemm"), ("splade_tail_codes", "prof_r02_tail_codes"),
+                    ("splade_rescore", "prof_r02_rescore")]}
+    for tag, rep in reps.get(rnd, reps["r02"]):
         path = os.path.join(SRC, rep + ".ncu-rep")
         if not os.path.exists(path):
             continue
@@ -78,7 +85,7 @@ def kernels(rnd):
             wr = float(r["dram__bytes_write.sum"][0].replace(",", "")) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1, "Tbyte": 1e12}.get(r["dram__bytes_write.sum"][1], 1)
             dur = float(r["gpu__time_duration.sum"][0].replace(",", "")) * {"ms": 1e-3, "us": 1e-6, "ns": 1e-9, "s": 1, "msecond": 1e-3, "usecond": 1e-6, "nsecond": 1e-9, "second": 1}.get(r["gpu__time_duration.sum"][1], 1)
             traffic[tag] = {"dram_bytes": rd + wr, "duration_s_under_ncu": dur, "grid": r.get("launch__grid_size", ("", ""))[0],
-                            "launch": "largest round of one step (ncu -s index in scripts/gpu_profile.sh)"}
+                            "round": rnd, "launch": f"largest round of one step (ncu -s index in scripts/gpu_profile{'_r02' if rnd != 'r01' else ''}.sh)"}
             print(tag, traffic[tag])
     if traffic:
         json.dump(traffic, open(os.path.join(OUT, "traffic.json"), "w"), indent=1)
