@@ -571,7 +571,11 @@ def main():
         algo["bm25_index_bytes"] = lexical.nbytes()
     if "splade" in systems:
         (dp, dt, dw), gen_s["splade"] = timed(lambda: make_splade(lo, hi, n_total, 120, 8, 512, 311, dev))
-        sparse, build_s["splade"] = timed(lambda: SparseIndex(dp, dt, dw, SPLADE_VOCAB, "cos_sim", device=dev, doc_base=lo))
+        # threshold bootstrap over the first docs of every shard: the SAME number on every rank (the round schedule, hence the
+        # collectives of the cross-shard threshold exchange, start there), at most 1/8 of the smallest shard
+        boot = min(262144, (n_total // world) // 8 // 256 * 256)
+        sparse, build_s["splade"] = timed(lambda: SparseIndex(dp, dt, dw, SPLADE_VOCAB, "cos_sim", device=dev, doc_base=lo,
+                                                              boot_docs=boot))
         del dp, dt, dw
         qp, qt, qw = make_splade(0, nq, nq, 24, 2, 64, 312, dev)
         q.sp_ptr, q.sp_term, q.sp_weight = sparse_queries(qp, qt, qw, "cos_sim", dev)

@@ -327,9 +327,10 @@ class SparseIndex:
             self._build_head_tail(row, term, w, head_dim, int(tail_tile_docs or SP_TAIL_TILE_DOCS))
             # threshold bootstrap (ops.splade_topk): a general index over the first boot_docs docs, when they are a small part
             # of the shard.  Sharded runs must pass the same boot_docs on every rank (the round schedule starts there).
+            explicit = boot_docs is not None
             boot_docs = SP_BOOT_DOCS if boot_docs is None else int(boot_docs)
             boot_docs = boot_docs // 256 * 256
-            if boot_docs >= 256 and self.n_docs >= 8 * boot_docs:
+            if boot_docs >= 256 and (self.n_docs >= 8 * boot_docs if not explicit else self.n_docs >= 2 * boot_docs):
                 self.head.boot = self._general_view(boot_docs)
 
     def _build_head_tail(self, row, term, w, head_dim, tail_tile_docs):
