@@ -187,7 +187,8 @@ static int dense_filter_phase(const void* q_bf16, const void* d_bf16, bool exact
     if (rc) return rc;
     static bool attr = false;
     if (!attr) {
-        FZ_CUDA(cudaFuncSetAttribute(filter_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
+        FZ_CUDA(cudaFuncSetAttribute(filter_gemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
+        FZ_CUDA(cudaFuncSetAttribute(filter_gemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
         attr = true;
     }
     GemmArgs G;
@@ -212,7 +213,8 @@ static int dense_filter_phase(const void* q_bf16, const void* d_bf16, bool exact
             const int max_clusters = num_sms() / kPair;
             const int grid = kPair * (int)(pair_tiles < max_clusters ? pair_tiles : max_clusters);
             ProfScope prof("dense_filter_gemm", stream);
-            filter_gemm_kernel<false><<<grid, kGemmThreads, kGemmSmem, stream>>>(tmap_q, tmap_d, G);
+            if (gemm_two_cta()) filter_gemm_kernel<false, true><<<grid, kGemmThreads, kGemmSmem, stream>>>(tmap_q, tmap_d, G);
+                else filter_gemm_kernel<false, false><<<grid, kGemmThreads, kGemmSmem, stream>>>(tmap_q, tmap_d, G);
         }
         FZ_LAUNCH_CHECK();
         const bool last = hi >= SN;

@@ -62,6 +62,18 @@ struct GemmArgs {
     const float2* qparam;        // [n_queries] (gh, g): head gain incl. the bf16 error allowance, tail gain
 };
 
+// FZ_GEMM_2CTA=1 selects the CTA-pair MMA (cta_group::2, M = 256) instead of the default cta_group::1 + multicast
+// variant.  Both are parity-green; the pair MMA halves the doc-tile bytes entering each SM but measured no faster
+// (DPR 95.9 vs 95.1 ms, SPLADE head 41.7 vs 37.6 ms): the kernel waits on the epilogue, not on operands.
+inline bool gemm_two_cta() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("FZ_GEMM_2CTA");
+        on = (e && e[0] == '1') ? 1 : 0;
+    }
+    return on == 1;
+}
+
 __device__ __forceinline__ float code_decode(uint32_t word, int nib) {
     const uint32_t sh = nib <= 5 ? (word << (22 - 4 * nib)) : (word >> (4 * nib - 22));
     return __uint_as_float((sh & (15u << 22)) | kCodeBase);
@@ -71,10 +83,16 @@ __device__ __forceinline__ float code_decode(uint32_t word, int nib) {
 // to both, so the pair moves 16 + 16 KB per k-block and CTA instead of 16 + 32 KB.  The kernel is bound by L2 -> SM
 // operand traffic (profiles/), and 55 query tiles asking L2 for the same doc tile at once also miss together.
 constexpr int kPair = 2;
-template <bool kCodes>
+// k2Cta: the pair executes ONE tcgen05.mma.cta_group::2 of M = 256 per k-step instead of two M = 128 MMAs on a multicast B
+// tile: each CTA then receives 16 KB (its queries) + 16 KB (its HALF of the doc tile) per k-block instead of 16 + 32 KB.
+// The kernel is bound by operand bytes entering the SM (48 KB per 128x256x64 k-block = 126 GB/s per SM at full tensor rate).
+template <bool kCodes, bool k2Cta = false>
 __global__ void __cluster_dims__(kPair, 1, 1) __launch_bounds__(kGemmThreads, 1)
 filter_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_d,
                    const GemmArgs G) {
+    constexpr int kStages = k2Cta ? 6 : fz::kStages;
+    constexpr int kBBytes = k2Cta ? fz::kBBytes / kPair : fz::kBBytes;
+    constexpr int kStageBytes = kABytes + kBBytes;
     extern __shared__ unsigned char smem_dyn[];
     // 1024-byte alignment: required by the 128-byte swizzle atoms the UMMA descriptors assume
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
@@ -99,17 +117,23 @@ filter_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < kStages; ++i) {
             ptx::mbar_init(&full_bar[i], 1);
-            ptx::mbar_init(&empty_bar[i], kPair);       // both CTAs of the pair must have consumed a multicast stage
+            // multicast: both CTAs' MMAs must have consumed a stage; 2-CTA: the leader's commit is the one arrival
+            ptx::mbar_init(&empty_bar[i], k2Cta ? 1 : kPair);
         }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&tfull_bar[i], 1);
-            ptx::mbar_init(&tempty_bar[i], 4);
+            ptx::mbar_init(&tempty_bar[i], k2Cta ? 8 : 4);      // 2-CTA: the epilogue warps of BOTH CTAs arrive on the leader's
         }
         ptx::fence_barrier_init();
     }
     if (warp == 2) {
-        ptx::tmem_alloc(tmem_slot, kTmemCols);
-        ptx::tmem_relinquish();
+        if constexpr (k2Cta) {
+            ptx::tmem_alloc_2cta(tmem_slot, kTmemCols);
+            ptx::tmem_relinquish_2cta();
+        } else {
+            ptx::tmem_alloc(tmem_slot, kTmemCols);
+            ptx::tmem_relinquish();
+        }
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -132,19 +156,26 @@ filter_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                     st_wait_empty += FZ_CLOCK() - t0;
                     unsigned char* sa = smem + (size_t)stage * kStageBytes;
-                    ptx::mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);     // own queries + both halves of the docs
-                    ptx::tma_load_2d(sa, &tmap_q, &full_bar[stage], kb * kBK, q0);
-                    ptx::tma_load_2d_multicast(sa + kABytes + crank * (kBBytes / kPair), &tmap_d, &full_bar[stage], kb * kBK,
-                                               (int32_t)(d0 + crank * (kBN / kPair)), (uint16_t)((1u << kPair) - 1));
+                    if constexpr (k2Cta) {
+                        // both CTAs' bytes are credited to the LEADER's barrier: it expects the pair's 2 x (A + half B)
+                        if (crank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], kPair * kStageBytes);
+                        ptx::tma_load_2d_2cta(sa, &tmap_q, &full_bar[stage], kb * kBK, q0);
+                        ptx::tma_load_2d_2cta(sa + kABytes, &tmap_d, &full_bar[stage], kb * kBK, (int32_t)(d0 + crank * (kBN / kPair)));
+                    } else {
+                        ptx::mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);     // own queries + both halves of the docs
+                        ptx::tma_load_2d(sa, &tmap_q, &full_bar[stage], kb * kBK, q0);
+                        ptx::tma_load_2d_multicast(sa + kABytes + crank * (kBBytes / kPair), &tmap_d, &full_bar[stage], kb * kBK,
+                                                   (int32_t)(d0 + crank * (kBN / kPair)), (uint16_t)((1u << kPair) - 1));
+                    }
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
             if (G.stats) G.stats[blockIdx.x * 8 + 0] += (unsigned long long)st_wait_empty;
         }
-    } else if (warp == 1) {
-        // ================================ MMA issuer (one elected lane) ===================================
+    } else if (warp == 1 && (!k2Cta || crank == 0)) {
+        // ================================ MMA issuer (one elected lane; 2-CTA: of the leader CTA only) =====
         if (ptx::elect_one()) {
-            const uint32_t idesc = ptx::make_idesc_bf16(kBM, kBN);
+            const uint32_t idesc = ptx::make_idesc_bf16(k2Cta ? kPair * kBM : kBM, kBN);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -168,14 +199,17 @@ filter_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
                     for (int k = 0; k < kBK / 16; ++k) {
                         const uint64_t da = ptx::make_smem_desc_sw128(sa + k * 32);
                         const uint64_t db = ptx::make_smem_desc_sw128(sb + k * 32);
-                        ptx::mma_bf16_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                        if constexpr (k2Cta) ptx::mma_bf16_ss_2cta(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                        else ptx::mma_bf16_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
                     // the stage is reusable once BOTH CTAs' MMAs on it have retired (either producer refills both copies)
-                    ptx::mma_commit_multicast(&empty_bar[stage], (uint16_t)((1u << kPair) - 1));
+                    if constexpr (k2Cta) ptx::mma_commit_2cta(&empty_bar[stage], (uint16_t)((1u << kPair) - 1));
+                    else ptx::mma_commit_multicast(&empty_bar[stage], (uint16_t)((1u << kPair) - 1));
                     st_issue += FZ_CLOCK() - t2;
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
-                ptx::mma_commit(&tfull_bar[buf]);           // accumulator complete
+                if constexpr (k2Cta) ptx::mma_commit_2cta(&tfull_bar[buf], (uint16_t)((1u << kPair) - 1));   // in both CTAs
+                else ptx::mma_commit(&tfull_bar[buf]);           // accumulator complete
             }
             if (G.stats) {
                 G.stats[blockIdx.x * 8 + 1] += (unsigned long long)st_wait_tempty;
@@ -274,7 +308,10 @@ filter_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
                 // append walks the set bits of the masks - work proportional to the survivors, not to the tile.
                 ptx::tc_fence_before();
                 __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&tempty_bar[buf]);
+                if (lane == 0) {
+                    if constexpr (k2Cta) ptx::mbar_arrive_cluster(&tempty_bar[buf], 0);
+                    else ptx::mbar_arrive(&tempty_bar[buf]);
+                }
                 int total = 0;
 #pragma unroll
                 for (int c = 0; c < kBN / 32; ++c) total += __popc(masks[c]);
@@ -328,9 +365,11 @@ filter_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
             const long long tp2 = FZ_CLOCK();
             // Pass 2: one atomic per thread and tile reserves the slots and the flagged chunks are read again.
             // tcgen05.ld is warp-collective, so the chunk loop runs over the warp-wide union of the flags.
-            // (Parking the survivors in shared memory to release the accumulator before the atomic round trip was
-            // measured SLOWER: the kernel is bound by L2 -> SM operand traffic, and a team cannot start its next tile
-            // before its appends have drained anyway.)
+            // Two alternatives were measured SLOWER at full size (95 -> 100-102 ms): parking the survivors in shared
+            // memory so that the accumulator is released before the atomic round trip, and additionally deferring a
+            // tile's atomic + appends until after the next tile's pass 1.  The late rounds (few survivors) already run at
+            // 0.87 of the measured cuBLAS rate; the loss sits in the early rounds, where most chunks hold survivors and
+            // the parking stores cost more than the second TMEM read they save.
             const uint32_t wflags = __reduce_or_sync(0xffffffffu, flags);
             if (wflags) {
                 int base = total > 0 ? atomicAdd(&G.st.cnt[q], total) : 0;
@@ -359,7 +398,10 @@ filter_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
             }
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&tempty_bar[buf]);
+            if (lane == 0) {
+                if constexpr (k2Cta) ptx::mbar_arrive_cluster(&tempty_bar[buf], 0);
+                else ptx::mbar_arrive(&tempty_bar[buf]);
+            }
         }
         if (G.stats && ew == 0 && lane == 0 && team == 0) {
             G.stats[blockIdx.x * 8 + 4] += (unsigned long long)st_wait_tfull;
@@ -371,7 +413,10 @@ filter_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     ptx::tc_fence_before();
     __syncthreads();
     ptx::cluster_sync();                 // no CTA leaves while its partner may still multicast into it
-    if (warp == 2) ptx::tmem_dealloc(tmem_base, kTmemCols);
+    if (warp == 2) {
+        if constexpr (k2Cta) ptx::tmem_dealloc_2cta(tmem_base, kTmemCols);
+        else ptx::tmem_dealloc(tmem_base, kTmemCols);
+    }
 }
 
 }  // namespace fz

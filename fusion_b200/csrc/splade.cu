@@ -216,7 +216,8 @@ int fz_splade_topk(const fz_postings_t* tail, const fz_splade_head_t* head, cons
     if (rc) return rc;
     static bool attr = false;
     if (!attr) {
-        FZ_CUDA(cudaFuncSetAttribute(filter_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
+        FZ_CUDA(cudaFuncSetAttribute(filter_gemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
+        FZ_CUDA(cudaFuncSetAttribute(filter_gemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
         attr = true;
     }
     GemmArgs G;
@@ -291,7 +292,8 @@ int fz_splade_topk(const fz_postings_t* tail, const fz_splade_head_t* head, cons
             const int grid = kPair * (int)(pair_tiles < max_clusters ? pair_tiles : max_clusters);
             {
                 ProfScope prof("splade_head_gemm", stream);
-                filter_gemm_kernel<true><<<grid, kGemmThreads, kGemmSmem, stream>>>(tmap_q, tmap_d, G);
+                if (gemm_two_cta()) filter_gemm_kernel<true, true><<<grid, kGemmThreads, kGemmSmem, stream>>>(tmap_q, tmap_d, G);
+                else filter_gemm_kernel<true, false><<<grid, kGemmThreads, kGemmSmem, stream>>>(tmap_q, tmap_d, G);
                 FZ_LAUNCH_CHECK();
             }
             rc = rescore(0);
