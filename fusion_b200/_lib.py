@@ -31,6 +31,12 @@ class Postings(C.Structure):
                 ("tile_docs", C.c_int32), ("n_tiles", C.c_int32), ("n_coarse", C.c_int32), ("n_docs", C.c_int64)]
 
 
+class BuildPlan(C.Structure):
+    """mirror of fz_build_plan_t"""
+    _fields_ = [("n_short", C.c_int64), ("n_tiled_entries", C.c_int64), ("dense_stride", C.c_int64), ("n_tiled", C.c_int32),
+                ("n_dense", C.c_int32), ("n_tiles", C.c_int32), ("n_coarse", C.c_int32)]
+
+
 class SpladeHead(C.Structure):
     """mirror of fz_splade_head_t"""
     _fields_ = [("head_bf16", C.c_void_p), ("term_head", C.c_void_p), ("term_max", C.c_void_p), ("doc_ptr", C.c_void_p),
@@ -73,6 +79,18 @@ SIGNATURES = {
     "fz_prune_topk": (_i, [_p, _i, _i, _i, _p, _p]),
     "fz_csr_count": (_i, [_p, _i, _i, _p, _p]),
     "fz_csr_fill": (_i, [_p, _i, _i, _p, _p, _p, _p]),
+    "fz_build_lexical_workspace_bytes": (_sz, [_i64, C.c_int32]),
+    "fz_build_lexical_plan": (_i, [_p, _p, _i64, _i64, C.c_int32, _p, _p, _sz, _p]),
+    "fz_build_lexical_fill": (_i, [_p, _i64, _i64, C.c_int32, _i64, _p, _p, _p, _p, _p, _sz, _p]),
+    "fz_build_term_major_workspace_bytes": (_sz, [_i64, C.c_int32]),
+    "fz_build_term_major": (_i, [_p, _p, _i64, _i64, C.c_int32, _p, _p, _p, _sz, _p]),
+    "fz_build_postings_workspace_bytes": (_sz, [C.c_int32]),
+    "fz_build_postings_plan": (_i, [_p, _p, C.c_int32, _i64, C.c_int32, _i64, _i64, _p, _p, _p, _p, _sz, _p]),
+    "fz_build_postings_fill": (_i, [_p, _p, _p, _i, C.c_int32, _i64, C.c_int32, _p, _p, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p,
+                                    _p, _sz, _p]),
+    "fz_build_csr_normalize": (_i, [_p, _p, _i64, _p, _p]),
+    "fz_build_term_stats": (_i, [_p, _p, _i64, C.c_int32, _p, _p, _p, _p]),
+    "fz_build_splade_head": (_i, [_p, _p, _p, _i64, _i64, _p, C.c_int32, _p, _p]),
     "fz_lexical_impacts": (_i, [_p, _p, _p, _p, _p, C.c_int32, _i64, _d, _d, _d, _i, _p, _p]),
     "fz_sparse_topk_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "fz_sparse_topk_f64": (_i, [_p, _p, _p, _i, _i, _i64, _i, _i, _i, _p, _p, _p, _p, _sz, _p, _p]),

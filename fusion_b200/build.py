@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfusion_b200.so")
 STAMP = os.path.join(HERE, ".libfusion_b200.stamp")
-SOURCES = ["select.cu", "fuse.cu", "metrics.cu", "textbuild.cu", "activations.cu", "sparse.cu", "dense.cu", "splade.cu", "maxsim.cu"]
+SOURCES = ["select.cu", "fuse.cu", "metrics.cu", "textbuild.cu", "activations.cu", "sparse.cu", "build.cu", "dense.cu", "splade.cu", "maxsim.cu"]
 NVCC_FLAGS = ([] if not os.environ.get("FZ_KERNEL_STATS") else ["-DFZ_KERNEL_STATS"]) + (
     [] if not os.environ.get("FZ_PREFETCH_SCATTER") else ["-DFZ_PREFETCH_SCATTER"]) + [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",

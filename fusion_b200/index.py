@@ -5,8 +5,9 @@
   * DenseIndex     [N, d] fp32 + bf16 copies, normalised for cos_sim                    <- src/retrievers/hybrid.py:101-103
   * TokenStore     ColBERT token embeddings [T, 128] bf16 + per-doc offsets             <- src/utils/colbert_ir.py:175-205 (index)
 
-Construction uses torch device ops for the data movement (sort / unique / cumsum); the arithmetic that must
-match the reference bit for bit (idf with math.log10, fp64 impacts) is done on the host / in the CUDA library.
+Construction goes through the library's ``fz_build_*`` entry points (csrc/build.cu: sort, CSR transpose, the three-form
+postings layout, SPLADE head matrix), so a non-Python host can build the same index; the arithmetic that must match the
+reference bit for bit (idf with math.log10, fp64 impacts) is done on the host / in the CUDA library.
 Every index covers a contiguous shard [doc_base, doc_base + n_docs) of the corpus; corpus-global statistics
 (N, df, sum of doc lengths) are passed in so that sharded BM25 scores equal the unsharded ones.
 """
@@ -42,132 +43,31 @@ def idf_table(df: np.ndarray, n_docs: int, variant: str) -> np.ndarray:
 
 
 def _term_major_csr(row_of_entry: torch.Tensor, term_of_entry: torch.Tensor, n_rows: int, n_terms: int):
-    """Sort (term, doc) pairs term-major / doc-ascending.  -> (order, term_ptr int64 [V+1])."""
-    key = term_of_entry.to(torch.int64) * n_rows + row_of_entry.to(torch.int64)
-    order = torch.argsort(key)
-    counts = torch.bincount(term_of_entry.to(torch.int64), minlength=n_terms)
-    term_ptr = torch.zeros(n_terms + 1, dtype=torch.int64, device=key.device)
-    term_ptr[1:] = torch.cumsum(counts, 0)
-    return order, term_ptr, counts
+    """Sort (term, doc) pairs term-major / doc-ascending (``fz_build_term_major``).  -> (order, term_ptr int64 [V+1])."""
+    order, term_ptr = ops.build_term_major(row_of_entry.to(torch.int32), term_of_entry.to(torch.int32), n_rows, n_terms)
+    return order, term_ptr, term_ptr[1:] - term_ptr[:-1]
 
 
 def build_postings(term_ptr: torch.Tensor, post_doc: torch.Tensor, post_val: torch.Tensor, n_docs: int, tile_docs: int,
-                   tiled_min: int | None = None, dense_frac: float = DENSE_FRAC,
-                   chunk_postings: int = 1 << 27) -> ops.PostingsView:
-    """Term-major CSR (doc-ascending inside a term) -> the three storage forms of ``fz_postings_t``.
+                   tiled_min: int | None = None, dense_frac: float = DENSE_FRAC) -> ops.PostingsView:
+    """Term-major CSR (doc-ascending inside a term) -> the three storage forms of ``fz_postings_t``, built on the device by
+    ``fz_build_postings_plan`` / ``fz_build_postings_fill`` (csrc/build.cu).
 
-    short  df < tiled_min: kept as (doc, value) pairs.
+    short  df < tiled_min: kept as (doc, value) pairs, plus coarse marks (postings of the term below tile 16*c).
     tiled  per (term, tile) segments of (uint16 tile-relative offset, value), padded to 4 with (tile_docs, 0) and ordered
            for conflict-free shared-memory scatter: the postings of a segment are dealt round-robin over the 32 banks
            (doc % 32), and that sequence is laid out so that lane l of a warp reads element l of a run of 32 with its
            j-th accumulate (a thread owns the postings of one 16-byte value vector: 4 fp32 or 2 fp64).
     dense  df >= dense_frac * n_docs: one value per document, zero where the term is absent.
     """
-    dev = post_doc.device
-    n_terms = term_ptr.numel() - 1
-    vec = 16 // post_val.element_size()                     # 4 fp32 weights / 2 fp64 impacts per 16-byte load
     if tile_docs % 4 or not (4 <= tile_docs <= 32768):      # (the K2 kernels take <= 8192; the SPLADE tail kernel 32768)
         raise FusionB200Error(f"tile_docs={tile_docs} must be a multiple of 4 in [4, 32768]")
-    n_tiles = (n_docs + tile_docs - 1) // tile_docs
-    df = term_ptr[1:] - term_ptr[:-1]
     if tiled_min is None:
         tiled_min = int(os.environ.get("FZ_TILED_MIN", 512))
-    dense_min = max(tiled_min, int(math.ceil(dense_frac * n_docs))) if dense_frac > 0 else (1 << 62)
-    is_dense = df >= dense_min
-    is_tiled = (df >= tiled_min) & ~is_dense
-    tiled_terms = torch.nonzero(is_tiled).flatten()
-    dense_terms = torch.nonzero(is_dense).flatten()
-    n_tiled, n_dense = tiled_terms.numel(), dense_terms.numel()
-    term_slot = torch.full((n_terms,), -1, dtype=torch.int32, device=dev)
-    term_slot[tiled_terms] = torch.arange(n_tiled, dtype=torch.int32, device=dev)
-    term_slot[dense_terms] = -2 - torch.arange(n_dense, dtype=torch.int32, device=dev)
-    slot_of_post = torch.repeat_interleave(term_slot, df)                       # int32 per posting
-
-    # ---- short lists
-    m = slot_of_post == -1
-    short_doc, short_val = post_doc[m].contiguous(), post_val[m].contiguous()
-    short_ptr = torch.zeros(n_terms + 1, dtype=torch.int64, device=dev)
-    short_ptr[1:] = torch.cumsum(torch.where(is_tiled | is_dense, torch.zeros_like(df), df), 0)
     if tiled_min > 65535:
         raise FusionB200Error("tiled_min must be <= 65535 (short-list offsets are 16 bits)")
-    # coarse marks: postings of the term below tile 64*c, so the kernel bisects a handful of postings, not the list
-    n_coarse = (n_tiles + ops.COARSE_TILES - 1) // ops.COARSE_TILES
-    st = torch.repeat_interleave(torch.arange(n_terms, device=dev), short_ptr[1:] - short_ptr[:-1])
-    bucket = short_doc.long() // (ops.COARSE_TILES * tile_docs)
-    cnt = torch.bincount(st * n_coarse + bucket, minlength=n_terms * n_coarse).view(n_terms, n_coarse)
-    coarse = torch.zeros((n_terms, n_coarse + 1), dtype=torch.int64, device=dev)
-    coarse[:, 1:] = torch.cumsum(cnt, 1)
-    short_coarse = torch.where(coarse >= (1 << 15), coarse - (1 << 16), coarse).to(torch.int16)     # uint16 payload
-    del st, bucket, cnt, coarse
-
-    # ---- dense rows
-    stride = n_tiles * tile_docs
-    dense_val = torch.zeros((n_dense, stride), dtype=post_val.dtype, device=dev)
-    if n_dense:
-        m = slot_of_post <= -2
-        dense_val[(-2 - slot_of_post[m]).long(), post_doc[m].long()] = post_val[m]
-
-    # ---- tiled segments
-    tiled_base = torch.zeros(n_tiled, dtype=torch.int64, device=dev)
-    tile_off = torch.zeros((n_tiled, n_tiles + 1), dtype=torch.int32, device=dev)
-    tiled_off = torch.zeros(0, dtype=torch.int16, device=dev)
-    tiled_val = torch.zeros(0, dtype=post_val.dtype, device=dev)
-    if n_tiled:
-        m = slot_of_post >= 0
-        r_all = slot_of_post[m].long()
-        d_all = post_doc[m].long()
-        v_all = post_val[m]
-        del m, slot_of_post
-        seg_len = torch.bincount(r_all * n_tiles + d_all // tile_docs, minlength=n_tiled * n_tiles)
-        seg_pad = (seg_len + 3) // 4 * 4
-        seg_start = torch.zeros(n_tiled * n_tiles + 1, dtype=torch.int64, device=dev)
-        seg_start[1:] = torch.cumsum(seg_pad, 0)
-        seg_first = torch.cumsum(seg_len, 0) - seg_len                              # first unpadded posting of a segment
-        total = int(seg_start[-1])
-        tiled_base = seg_start[:-1:n_tiles].clone()
-        rel = seg_start.view(-1)[: n_tiled * n_tiles].view(n_tiled, n_tiles) - tiled_base[:, None]
-        last = seg_start[n_tiles::n_tiles] - tiled_base
-        if int(torch.max(last)) >= (1 << 32):
-            raise FusionB200Error("a tiled posting list exceeds 2^32 entries")
-        tile_off = torch.cat([rel, last[:, None]], dim=1).to(torch.int64)
-        tile_off = torch.where(tile_off >= (1 << 31), tile_off - (1 << 32), tile_off).to(torch.int32)   # uint32 payload
-        tiled_off = torch.full((total,), tile_docs, dtype=torch.int16, device=dev)
-        tiled_val = torch.zeros(total, dtype=post_val.dtype, device=dev)
-        # chunk over term rows so the sort temporaries stay bounded
-        df_t = df[tiled_terms]
-        row_end = torch.cumsum(df_t, 0).cpu().numpy()
-        r0, p0 = 0, 0
-        while r0 < n_tiled:
-            r1 = int(np.searchsorted(row_end, p0 + chunk_postings, side="right"))
-            r1 = min(n_tiled, max(r1, r0 + 1))
-            p1 = int(row_end[r1 - 1])
-            r, d, v = r_all[p0:p1], d_all[p0:p1], v_all[p0:p1]
-            tile = d // tile_docs
-            off = d - tile * tile_docs
-            seg = r * n_tiles + tile                                                # global segment id, non-decreasing
-            bank = off & 31
-            o1 = torch.sort(seg * 32 + bank, stable=True).indices                  # (segment, bank), offsets ascending
-            sb = (seg * 32 + bank)[o1]
-            pos = torch.arange(p1 - p0, device=dev)
-            is_start = torch.ones_like(sb, dtype=torch.bool)
-            is_start[1:] = sb[1:] != sb[:-1]
-            start_pos = torch.cummax(torch.where(is_start, pos, torch.zeros_like(pos)), 0).values
-            rank_in_bank = torch.empty_like(pos)
-            rank_in_bank[o1] = pos - start_pos
-            del sb, is_start, start_pos, o1
-            o2 = torch.sort(((seg << 16) | rank_in_bank) * 32 + bank).indices      # round-robin over the banks
-            q = torch.empty_like(pos)
-            q[o2] = pos - (seg_first[seg[o2]] - p0)
-            del o2, rank_in_bank
-            # a thread owns `vec` consecutive postings (one 16-byte vector of values): element e of the round-robin
-            # sequence goes to slot vec * (e mod P/vec) + e div (P/vec), so the lanes' j-th accumulates read a run of it
-            part = seg_pad[seg] // vec
-            dest = seg_start[seg] + vec * (q % part) + q // part
-            tiled_off[dest] = off.to(torch.int16)
-            tiled_val[dest] = v
-            r0, p0 = r1, p1
-    return ops.PostingsView(short_ptr, short_doc, short_val, short_coarse, term_slot, tiled_base, tile_off, tiled_off, tiled_val,
-                            dense_val, n_docs, tile_docs)
+    dense_min = max(tiled_min, int(math.ceil(dense_frac * n_docs))) if dense_frac > 0 else (1 << 62)
+    return ops.build_postings(term_ptr, post_doc, post_val, n_docs, tile_docs, tiled_min, dense_min)
 
 
 class LexicalIndex:
@@ -183,20 +83,13 @@ class LexicalIndex:
         self.device = torch.device(device)
         self.vocab_size, self.doc_base, self.tile_docs = int(vocab_size), int(doc_base), int(tile_docs)
         self.tiled_min, self.dense_frac = tiled_min, dense_frac
-        doc_ptr = torch.as_tensor(doc_ptr, dtype=torch.int64, device=self.device)
-        doc_tok = torch.as_tensor(doc_tok, device=self.device).to(torch.int64)
+        doc_ptr = torch.as_tensor(doc_ptr, dtype=torch.int64, device=self.device).contiguous()
+        doc_tok = torch.as_tensor(doc_tok, device=self.device).to(torch.int32).contiguous()
         self.n_docs = doc_ptr.numel() - 1
         lens = doc_ptr[1:] - doc_ptr[:-1]
-        self.doc_len = lens.to(torch.int32)
-        doc_of_tok = torch.repeat_interleave(torch.arange(self.n_docs, device=self.device), lens)
-        ukey, tf = torch.unique(doc_tok * self.n_docs + doc_of_tok, return_counts=True)   # sorted (term, doc)
-        self.post_doc = (ukey % self.n_docs).to(torch.int32)
-        post_term = ukey // self.n_docs
-        self.post_tf = tf.to(torch.int32)
-        df_local = torch.bincount(post_term, minlength=self.vocab_size)
-        self.term_ptr = torch.zeros(self.vocab_size + 1, dtype=torch.int64, device=self.device)
-        self.term_ptr[1:] = torch.cumsum(df_local, 0)
-        del ukey, tf, post_term, doc_of_tok
+        # (term, doc, tf) postings, term-major / doc-ascending: fz_build_lexical_* (device sort + run lengths)
+        self.term_ptr, self.post_doc, self.post_tf, self.doc_len = ops.build_lexical_postings(doc_ptr, doc_tok, self.vocab_size)
+        df_local = self.term_ptr[1:] - self.term_ptr[:-1]
         # corpus-global statistics (bm25.py:133-147): N, df, avgdl = statistics.mean(doc_len)
         if stats_reduce is not None:     # sharded build: (n_local, df_local, sum_dl_local) -> corpus-global values
             global_n_docs, global_df, global_sum_dl = stats_reduce(self.n_docs, df_local.cpu().numpy(), int(lens.sum()))
@@ -313,13 +206,15 @@ class SparseIndex:
         self.n_docs = self.doc_ptr.numel() - 1
         lens = self.doc_ptr[1:] - self.doc_ptr[:-1]
         row = torch.repeat_interleave(torch.arange(self.n_docs, device=self.device, dtype=torch.int32), lens)
+        term = term.contiguous()
         if similarity == "cos_sim":
-            sq = torch.zeros(self.n_docs, dtype=torch.float32, device=self.device).index_add_(0, row, w * w)
-            w = w / torch.clamp(torch.sqrt(sq), min=1e-12)[row.long()]
-            del sq
+            w = ops.build_csr_normalize(self.doc_ptr, w.contiguous())
         # doc-major copy: (int32 term, float weight) pairs, 8 bytes per posting
         self.doc_post = torch.stack([term, w.view(torch.int32)], dim=1).contiguous()
-        self.nonneg = bool((w >= 0).all()) if w.numel() else True
+        self._df, self._term_max, flags = ops.build_term_stats(term, w.contiguous(), self.vocab_size)
+        if flags & 2:
+            raise FusionB200Error("a term id lies outside [0, vocab_size)")
+        self.nonneg = not (flags & 1)
         self._view = None
         self.head = None
         head_dim = SP_HEAD_DIM if head_dim is None else int(head_dim)
@@ -337,19 +232,16 @@ class SparseIndex:
         dev, n, v = self.device, self.n_docs, self.vocab_size
         if head_dim % 64 or not (64 <= head_dim <= 256):
             raise FusionB200Error(f"head_dim={head_dim} must be 64, 128, 192 or 256")
-        df = torch.bincount(term.long(), minlength=v)
+        df = self._df
         n_head = min(head_dim, int((df > 0).sum()))
         head_terms = torch.topk(df, n_head).indices if n_head else torch.zeros(0, dtype=torch.int64, device=dev)
         term_head = torch.full((v,), -1, dtype=torch.int32, device=dev)
         term_head[head_terms] = torch.arange(n_head, dtype=torch.int32, device=dev)
-        term_max = torch.zeros(v, dtype=torch.float32, device=dev).scatter_reduce_(0, term.long(), w, "amax", include_self=True)
-        th = term_head[term.long()]
-        m = th >= 0
-        head = torch.zeros((n, head_dim), dtype=torch.bfloat16, device=dev)
-        head[row[m].long(), th[m].long()] = w[m].to(torch.bfloat16)
-        m = ~m
+        term_max = self._term_max
+        head = ops.build_splade_head(self.doc_ptr, term, w.contiguous(), term_head, head_dim)
+        m = term_head[term.long()] < 0
         row_t, term_t, w_t = row[m], term[m], w[m]
-        del th, m
+        del m
         order, term_ptr_t, _ = _term_major_csr(row_t, term_t, n, v)
         tail_tile_docs = max(256, min(tail_tile_docs, (n + 255) // 256 * 256))
         # (tail tiles are small: terms rarer than one posting per tile stay plain doc-ascending lists with coarse marks)

@@ -561,6 +561,113 @@ def lexical_impacts(term_ptr, post_doc, post_tf, doc_len, idf, avgdl: float, k1:
     return out
 
 
+# ----------------------------------------------------------------------------------------------- index build
+def build_lexical_postings(doc_ptr: torch.Tensor, doc_tok: torch.Tensor, vocab: int):
+    """Token ids per document -> term-major postings: (term_ptr int64 [V+1], post_doc int32, post_tf int32, doc_len int32)
+    (``fz_build_lexical_*``; the reference builds dicts, bm25.py:53-83)."""
+    lib = _lib.load()
+    doc_ptr = _req(doc_ptr, torch.int64, "doc_ptr")
+    doc_tok = _req(doc_tok, torch.int32, "doc_tok")
+    dev = doc_ptr.device
+    n_docs, n_tok = doc_ptr.numel() - 1, doc_tok.numel()
+    nbytes = lib.fz_build_lexical_workspace_bytes(n_tok, vocab)
+    ws = _ws(nbytes, dev)
+    nnz = C.c_int64(0)
+    check(lib.fz_build_lexical_plan(_ptr(doc_ptr), _ptr(doc_tok), n_docs, n_tok, vocab, C.byref(nnz), _ptr(ws), nbytes,
+                                    _stream(doc_ptr)), "fz_build_lexical_plan")
+    nnz = int(nnz.value)
+    term_ptr = torch.empty(vocab + 1, dtype=torch.int64, device=dev)
+    post_doc = torch.empty(nnz, dtype=torch.int32, device=dev)
+    post_tf = torch.empty(nnz, dtype=torch.int32, device=dev)
+    doc_len = torch.empty(n_docs, dtype=torch.int32, device=dev)
+    check(lib.fz_build_lexical_fill(_ptr(doc_ptr), n_docs, n_tok, vocab, nnz, _ptr(term_ptr), _ptr(post_doc), _ptr(post_tf),
+                                    _ptr(doc_len), _ptr(ws), nbytes, _stream(doc_ptr)), "fz_build_lexical_fill")
+    return term_ptr, post_doc, post_tf, doc_len
+
+
+def build_term_major(row: torch.Tensor, term: torch.Tensor, n_rows: int, n_terms: int):
+    """(row, term) per entry -> (order int64 [nnz]: entry indices term-major / row-ascending, term_ptr int64 [V+1])."""
+    lib = _lib.load()
+    row, term = _req(row, torch.int32, "row"), _req(term, torch.int32, "term")
+    dev, nnz = row.device, row.numel()
+    nbytes = lib.fz_build_term_major_workspace_bytes(nnz, n_terms)
+    ws = _ws(nbytes, dev)
+    term_ptr = torch.empty(n_terms + 1, dtype=torch.int64, device=dev)
+    order = torch.empty(nnz, dtype=torch.int64, device=dev)
+    check(lib.fz_build_term_major(_ptr(row), _ptr(term), nnz, n_rows, n_terms, _ptr(term_ptr), _ptr(order), _ptr(ws), nbytes,
+                                  _stream(row)), "fz_build_term_major")
+    return order, term_ptr
+
+
+def build_postings(term_ptr: torch.Tensor, post_doc: torch.Tensor, post_val: torch.Tensor, n_docs: int, tile_docs: int,
+                   tiled_min: int, dense_min: int) -> "PostingsView":
+    """Term-major CSR -> the three storage forms of ``fz_postings_t`` (``fz_build_postings_plan`` / ``_fill``)."""
+    lib = _lib.load()
+    term_ptr = _req(term_ptr, torch.int64, "term_ptr")
+    post_doc = _req(post_doc, torch.int32, "post_doc")
+    if post_val.dtype not in (torch.float32, torch.float64):
+        raise FusionB200Error(f"post_val must be float32 or float64, got {post_val.dtype}")
+    post_val = _req(post_val, post_val.dtype, "post_val")
+    dev, n_terms, nnz = term_ptr.device, term_ptr.numel() - 1, post_doc.numel()
+    nbytes = lib.fz_build_postings_workspace_bytes(n_terms)
+    ws = _ws(nbytes, dev)
+    short_ptr = torch.empty(n_terms + 1, dtype=torch.int64, device=dev)
+    term_slot = torch.empty(n_terms, dtype=torch.int32, device=dev)
+    plan = _lib.BuildPlan()
+    check(lib.fz_build_postings_plan(_ptr(term_ptr), _ptr(post_doc), n_terms, n_docs, tile_docs, int(tiled_min), int(dense_min),
+                                     _ptr(short_ptr), _ptr(term_slot), C.byref(plan), _ptr(ws), nbytes, _stream(term_ptr)),
+          "fz_build_postings_plan")
+    vt = post_val.dtype
+    short_doc = torch.empty(plan.n_short, dtype=torch.int32, device=dev)
+    short_val = torch.empty(plan.n_short, dtype=vt, device=dev)
+    short_coarse = torch.empty((n_terms, plan.n_coarse + 1), dtype=torch.int16, device=dev)
+    tiled_base = torch.empty(plan.n_tiled, dtype=torch.int64, device=dev)
+    tile_off = torch.empty((plan.n_tiled, plan.n_tiles + 1), dtype=torch.int32, device=dev)
+    tiled_off = torch.empty(plan.n_tiled_entries, dtype=torch.int16, device=dev)
+    tiled_val = torch.empty(plan.n_tiled_entries, dtype=vt, device=dev)
+    dense_val = torch.empty((plan.n_dense, plan.dense_stride), dtype=vt, device=dev)
+    check(lib.fz_build_postings_fill(_ptr(term_ptr), _ptr(post_doc), _ptr(post_val), post_val.element_size(), n_terms, n_docs,
+                                     tile_docs, _ptr(short_ptr), _ptr(term_slot), C.byref(plan), nnz, _ptr(short_doc),
+                                     _ptr(short_val), _ptr(short_coarse), _ptr(tiled_base), _ptr(tile_off), _ptr(tiled_off),
+                                     _ptr(tiled_val), _ptr(dense_val), _ptr(ws), nbytes, _stream(term_ptr)),
+          "fz_build_postings_fill")
+    return PostingsView(short_ptr, short_doc, short_val, short_coarse, term_slot, tiled_base, tile_off, tiled_off, tiled_val,
+                        dense_val, n_docs, tile_docs)
+
+
+def build_csr_normalize(doc_ptr: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    out = torch.empty_like(weight)
+    check(lib.fz_build_csr_normalize(_ptr(_req(doc_ptr, torch.int64, "doc_ptr")), _ptr(_req(weight, torch.float32, "weight")),
+                                     doc_ptr.numel() - 1, _ptr(out), _stream(weight)), "fz_build_csr_normalize")
+    return out
+
+
+def build_term_stats(term: torch.Tensor, weight: torch.Tensor, n_terms: int):
+    """-> (df int64 [V], term_max float32 [V], flags int: 1 = negative weight present, 2 = term id out of range)."""
+    lib = _lib.load()
+    term, weight = _req(term, torch.int32, "term"), _req(weight, torch.float32, "weight")
+    dev = term.device
+    df = torch.empty(n_terms, dtype=torch.int64, device=dev)
+    tmax = torch.empty(n_terms, dtype=torch.float32, device=dev)
+    flags = torch.empty(1, dtype=torch.int32, device=dev)
+    check(lib.fz_build_term_stats(_ptr(term), _ptr(weight), term.numel(), n_terms, _ptr(df), _ptr(tmax), _ptr(flags),
+                                  _stream(term)), "fz_build_term_stats")
+    return df, tmax, int(flags.item())
+
+
+def build_splade_head(doc_ptr: torch.Tensor, term: torch.Tensor, weight: torch.Tensor, term_head: torch.Tensor,
+                      head_dim: int) -> torch.Tensor:
+    lib = _lib.load()
+    n_docs = doc_ptr.numel() - 1
+    head = torch.empty((n_docs, head_dim), dtype=torch.bfloat16, device=doc_ptr.device)
+    check(lib.fz_build_splade_head(_ptr(_req(doc_ptr, torch.int64, "doc_ptr")), _ptr(_req(term, torch.int32, "term")),
+                                   _ptr(_req(weight, torch.float32, "weight")), n_docs, term.numel(),
+                                   _ptr(_req(term_head, torch.int32, "term_head")), head_dim, _ptr(head), _stream(term)),
+          "fz_build_splade_head")
+    return head
+
+
 # ----------------------------------------------------------------------------------------------- K1
 def normalize_rows(x: torch.Tensor, normalize: bool = True, want_f32: bool = True, want_bf16: bool = True):
     """rows / max(||row||, 1e-12) -> (fp32 copy | None, bf16 copy | None)."""

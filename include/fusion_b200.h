@@ -243,6 +243,68 @@ int fz_lexical_impacts(const int64_t* term_ptr, const int32_t* post_doc, const i
                        const double* idf, int32_t n_terms, int64_t nnz, double avgdl, double k1, double b, int variant,
                        double* out_impact, fz_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Index build ("fz_build_*"): everything between "token ids / sparse vectors per document" and the
+ * device arrays the scoring kernels read, so that a non-Python host can build an index.  Replaces the dict-of-dicts
+ * index construction of the reference: TFIDF._build_index + BM25._build_index (src/retrievers/bm25.py:53-83,141-143:
+ * vocabulary df, per-doc term frequencies, document lengths) and, for SPLADE, the [N, V] activation matrix of
+ * splade/base.py:186-197 (held here as CSR and turned into an inverted index).  All pointers are device pointers unless
+ * the name ends in _h.  Every builder is "plan -> the caller allocates -> fill": a *_plan call returns the array sizes
+ * to the host and synchronises the stream once; nothing in the library allocates device memory.  The plan and the fill
+ * call of one build must be given the SAME workspace, untouched in between (the plan leaves its sort / scan results there).
+ *
+ * fz_build_lexical_*   token ids per document (doc_ptr [n_docs + 1], doc_tok [n_tokens] in [0, vocab)) -> term-major
+ *                      postings (term_ptr [vocab + 1], post_doc, post_tf: doc-ascending inside a term, tf = occurrences of
+ *                      the term in the doc) and doc_len [n_docs].  plan returns nnz = distinct (term, doc) pairs.
+ * fz_build_term_major  (row, term) per entry of a doc-major CSR -> term_ptr [n_terms + 1] and the permutation out_order
+ *                      [nnz] (entry indices in term-major / row-ascending order) - the transpose used for SPLADE vectors.
+ * fz_build_postings_*  term-major CSR (term_ptr, post_doc ascending inside a term, post_val float or double) -> the three
+ *                      storage forms of fz_postings_t.  tiled_min / dense_min: df from which a term is stored as tile
+ *                      segments / as a dense row (dense_min = 2^62: never).  plan writes short_ptr (= fz_postings_t.term_ptr)
+ *                      and term_slot and returns the sizes of the other arrays:
+ *                        post_doc / post_val [n_short]; short_coarse [n_terms, n_coarse + 1]; tiled_base [n_tiled];
+ *                        tiled_tile_off [n_tiled, n_tiles + 1]; tiled_off / tiled_val [n_tiled_entries];
+ *                        dense_val [n_dense, dense_stride].
+ * fz_build_csr_normalize   w / max(|row|_2, 1e-12) per CSR row (cos_sim: hybrid.py:101-103 normalises both sides)
+ * fz_build_term_stats      df [n_terms] and the largest weight of every term (0 for unused terms); out_flags (device
+ *                          int32): bit 0 = a negative weight exists (no head/tail split), bit 1 = a term id out of range
+ * fz_build_splade_head     the head matrix of fz_splade_head_t: head[d, term_head[t]] = bf16(w) for the head terms
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct fz_build_plan {
+    int64_t n_short;         /* postings kept as short lists */
+    int64_t n_tiled_entries; /* tile-segment entries incl. padding */
+    int64_t dense_stride;    /* n_tiles * tile_docs */
+    int32_t n_tiled;
+    int32_t n_dense;
+    int32_t n_tiles;
+    int32_t n_coarse;
+} fz_build_plan_t;
+
+size_t fz_build_lexical_workspace_bytes(int64_t n_tokens, int32_t vocab);
+int fz_build_lexical_plan(const int64_t* doc_ptr, const int32_t* doc_tok, int64_t n_docs, int64_t n_tokens, int32_t vocab,
+                          int64_t* out_nnz_h, void* ws, size_t ws_bytes, fz_stream_t stream);
+int fz_build_lexical_fill(const int64_t* doc_ptr, int64_t n_docs, int64_t n_tokens, int32_t vocab, int64_t nnz,
+                          int64_t* out_term_ptr, int32_t* out_post_doc, int32_t* out_post_tf, int32_t* out_doc_len, void* ws,
+                          size_t ws_bytes, fz_stream_t stream);
+size_t fz_build_term_major_workspace_bytes(int64_t nnz, int32_t n_terms);
+int fz_build_term_major(const int32_t* row, const int32_t* term, int64_t nnz, int64_t n_rows, int32_t n_terms,
+                        int64_t* out_term_ptr, int64_t* out_order, void* ws, size_t ws_bytes, fz_stream_t stream);
+size_t fz_build_postings_workspace_bytes(int32_t n_terms);
+int fz_build_postings_plan(const int64_t* term_ptr, const int32_t* post_doc, int32_t n_terms, int64_t n_docs, int32_t tile_docs,
+                           int64_t tiled_min, int64_t dense_min, int64_t* out_short_ptr, int32_t* out_term_slot,
+                           fz_build_plan_t* out_plan_h, void* ws, size_t ws_bytes, fz_stream_t stream);
+int fz_build_postings_fill(const int64_t* term_ptr, const int32_t* post_doc, const void* post_val, int value_bytes,
+                           int32_t n_terms, int64_t n_docs, int32_t tile_docs, const int64_t* short_ptr,
+                           const int32_t* term_slot, const fz_build_plan_t* plan_h, int64_t nnz, int32_t* out_short_doc,
+                           void* out_short_val, uint16_t* out_short_coarse, int64_t* out_tiled_base,
+                           uint32_t* out_tiled_tile_off, uint16_t* out_tiled_off, void* out_tiled_val, void* out_dense_val,
+                           void* ws, size_t ws_bytes, fz_stream_t stream);
+int fz_build_csr_normalize(const int64_t* doc_ptr, const float* weight, int64_t n_docs, float* out_weight, fz_stream_t stream);
+int fz_build_term_stats(const int32_t* term, const float* weight, int64_t nnz, int32_t n_terms, int64_t* out_df,
+                        float* out_term_max, int32_t* out_flags, fz_stream_t stream);
+int fz_build_splade_head(const int64_t* doc_ptr, const int32_t* term, const float* weight, int64_t n_docs, int64_t nnz,
+                         const int32_t* term_head, int32_t head_dim, void* out_head_bf16, fz_stream_t stream);
+
 /* top-k: out [n_queries, k] (score desc, ties by lower doc id); zero-score docs fill up in doc-id order.
  *   q_ptr [n_queries+1], q_term [nq] (term ids in query-token order, duplicates kept, -1 = out of vocabulary;
  *   at most FZ_MAX_QUERY_TERMS per query: a longer query gets FZ_STATUS_TOO_LONG in out_status and an unspecified row -

@@ -63,14 +63,16 @@ def test_header_is_plain_c_and_layouts_match_ctypes(tmp_path):
         pytest.skip("no gcc")
     src = tmp_path / "hdr_check.c"
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "fusion_b200.h"\n'
-                   'int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(fz_shard_sync_t), offsetof(fz_shard_sync_t, n_shards),\n'
+                   'int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(fz_shard_sync_t), offsetof(fz_shard_sync_t, n_shards),\n'
                    '  offsetof(fz_shard_sync_t, floor_rank), offsetof(fz_shard_sync_t, sched_docs), sizeof(fz_postings_t),\n'
                    '  offsetof(fz_postings_t, n_docs), offsetof(fz_postings_t, dense_stride), sizeof(fz_splade_head_t),\n'
-                   '  offsetof(fz_splade_head_t, head_dim), offsetof(fz_splade_head_t, flags)); return 0; }\n')
+                   '  offsetof(fz_splade_head_t, head_dim), offsetof(fz_splade_head_t, flags), sizeof(fz_build_plan_t),\n'
+                   '  offsetof(fz_build_plan_t, n_tiled), offsetof(fz_build_plan_t, n_coarse)); return 0; }\n')
     exe = tmp_path / "hdr_check"
     subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     assert got == [ctypes.sizeof(_lib.ShardSync), _lib.ShardSync.n_shards.offset, _lib.ShardSync.floor_rank.offset,
                    _lib.ShardSync.sched_docs.offset, ctypes.sizeof(_lib.Postings), _lib.Postings.n_docs.offset,
                    _lib.Postings.dense_stride.offset, ctypes.sizeof(_lib.SpladeHead), _lib.SpladeHead.head_dim.offset,
-                   _lib.SpladeHead.flags.offset]
+                   _lib.SpladeHead.flags.offset, ctypes.sizeof(_lib.BuildPlan), _lib.BuildPlan.n_tiled.offset,
+                   _lib.BuildPlan.n_coarse.offset]

@@ -1,12 +1,13 @@
-"""CPU checks of the three-form postings layout (fusion_b200.index.build_postings): the builder is plain torch, so the
-layout the CUDA kernel consumes can be verified without a GPU - every posting present exactly once, segments padded
-and aligned as the vectorised loads need, and the bank ordering doing its job."""
+"""CPU checks of the three-form postings layout on its torch specification (tests/_torch_postings.py): the layout the
+scoring kernels consume can be verified without a GPU - every posting present exactly once, segments padded and aligned
+as the vectorised loads need, and the bank ordering doing its job.  tests/test_gpu_build.py then holds the device
+builder (fz_build_postings_*) to this specification array for array."""
 import numpy as np
 import pytest
 import torch
 
 from fusion_b200 import synth
-from fusion_b200.index import build_postings
+from _torch_postings import build_postings
 
 
 def _csr(n_docs, vocab, seed, mean_len=40):
