@@ -574,6 +574,7 @@ def main():
         # threshold bootstrap over the first docs of every shard: the SAME number on every rank (the round schedule, hence the
         # collectives of the cross-shard threshold exchange, start there), at most 1/8 of the smallest shard
         boot = min(262144, (n_total // world) // 8 // 256 * 256)
+        boot = int(os.environ.get("FZ_BENCH_BOOT", boot))      # tuning knob (same value on every rank)
         sparse, build_s["splade"] = timed(lambda: SparseIndex(dp, dt, dw, SPLADE_VOCAB, "cos_sim", device=dev, doc_base=lo,
                                                               boot_docs=boot))
         del dp, dt, dw

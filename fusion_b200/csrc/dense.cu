@@ -198,6 +198,7 @@ static int dense_filter_phase(const void* q_bf16, const void* d_bf16, bool exact
     G.m_tiles = ceil_div(n_queries, kBM);
     G.st = cand_state_carve<float>(ws, n_queries, cap, out_status);
     G.stats = (unsigned long long*)g_debug_stats;
+    if (const char* e = getenv("FZ_DEBUG_GEMM")) G.debug = atoi(e);
     rc = cand_init<float>(G.st, n_queries, stream);
     if (rc) return rc;
     const bool synced = sync && sync->hook;

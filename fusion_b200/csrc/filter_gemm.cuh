@@ -39,7 +39,8 @@ constexpr int kBBytes = kBN * kBK * 2;   // 32 KB
 constexpr int kStageBytes = kABytes + kBBytes;
 constexpr int kGemmThreads = 384;        // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps 4-7 / 8-11 two epilogue teams
 constexpr int kTmemCols = 512;           // two 256-column fp32 accumulators
-constexpr size_t kGemmSmem = (size_t)kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int kScratchBytes = 256 * 32 * 4;   // plain mode: one 32-column chunk per epilogue thread (pass 2)
+constexpr size_t kGemmSmem = (size_t)kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kScratchBytes;
 
 // ---- 4-bit tail codes (kCodes): decode(c) = as_float(kCodeBase | c << 22) = B0 * 2^(c >> 1) * (1 + (c & 1) / 2),
 // B0 = 2^-7.  The bound a code stands for is decode(c) - B0 (in units of 1 / g of the query): 0, .5, 1, 2, 3, 5, 7, 11,
@@ -56,6 +57,7 @@ struct GemmArgs {
     int m_tiles, n_tiles;
     CandState<float> st;
     unsigned long long* stats;   // optional [gridDim.x, 8] cycle counters (fz_debug_set_stats)
+    int debug;                   // FZ_DEBUG_GEMM timing probes (results are WRONG): 1 = nothing passes, 2 = no appends
     // kCodes only
     const uint4* codes;          // [(n_tiles * 8 + chunk) * q_pad + q]: the 32 codes of (query q, 32-doc chunk)
     int q_pad;                   // n_queries rounded up to kBM
@@ -102,6 +104,7 @@ filter_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     uint64_t* tfull_bar = bars + 2 * kStages;      // [2]        MMA -> epilogue
     uint64_t* tempty_bar = bars + 2 * kStages + 2; // [2]        epilogue -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+    float* scratch = reinterpret_cast<float*>(smem + (size_t)kStages * kStageBytes + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // tile schedule: the cluster walks (doc tile, pair of query tiles); this CTA takes query tile 2 * pair + rank
@@ -251,7 +254,7 @@ filter_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
                     thr = -std::numeric_limits<float>::infinity();
                 }
             } else {
-                thr = tau;
+                thr = G.debug == 1 ? std::numeric_limits<float>::infinity() : tau;
             }
         };
         float thr_next, gh_next;
@@ -315,7 +318,7 @@ filter_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
                 int total = 0;
 #pragma unroll
                 for (int c = 0; c < kBN / 32; ++c) total += __popc(masks[c]);
-                if (total > 0) {
+                if (total > 0 && G.debug != 2) {
                     const long long tp2 = FZ_CLOCK();
                     int base = atomicAdd(&G.st.cnt[q], total);
                     int32_t* ids = G.st.id + (size_t)q * G.st.cap;
@@ -336,6 +339,7 @@ filter_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
             }
             // Pass 1: each 32-column chunk is reduced with a max TREE (no dependent chain) while the next chunk's
             // tcgen05.ld is already in flight; only a chunk whose maximum beats tau pays for the compare mask.
+            uint32_t masks[kBN / 32];
             uint32_t flags = 0;
             int total = 0;
             ptx::tmem_ld_32x32(t_row, ra);
@@ -351,45 +355,50 @@ filter_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
                                   fmaxf(__uint_as_float(cur[j + 16]), __uint_as_float(cur[j + 24])));
                 const float mx = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])),
                                        fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
+                uint32_t mask = 0;
                 if (mx > tau) {
-                    uint32_t mask = 0;
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
                         if (__uint_as_float(cur[j]) > tau && c * 32 + j < limit) mask |= 1u << j;
-                    if (mask) {
-                        flags |= 1u << c;
-                        total += __popc(mask);
-                    }
+                }
+                masks[c] = mask;
+                if (mask) {
+                    flags |= 1u << c;
+                    total += __popc(mask);
                 }
             }
             const long long tp2 = FZ_CLOCK();
-            // Pass 2: one atomic per thread and tile reserves the slots and the flagged chunks are read again.
-            // tcgen05.ld is warp-collective, so the chunk loop runs over the warp-wide union of the flags.
-            // Two alternatives were measured SLOWER at full size (95 -> 100-102 ms): parking the survivors in shared
-            // memory so that the accumulator is released before the atomic round trip, and additionally deferring a
-            // tile's atomic + appends until after the next tile's pass 1.  The late rounds (few survivors) already run at
-            // 0.87 of the measured cuBLAS rate; the loss sits in the early rounds, where most chunks hold survivors and
-            // the parking stores cost more than the second TMEM read they save.
-            const uint32_t wflags = __reduce_or_sync(0xffffffffu, flags);
+            // Pass 2: one atomic per thread and tile reserves the slots; the flagged chunks (warp-wide union: tcgen05.ld is
+            // warp-collective) are read again, double-buffered.  A lane with survivors in the chunk drops its 32 values
+            // into its private shared-memory scratch and walks the SET BITS of its mask, so the work is proportional to the
+            // survivors.  (The previous form tested all 32 columns of every flagged chunk behind 32 divergent branches and
+            // serialised the re-reads: with the exactness margin most chunks are flagged, and pass 2 took 9k of the 12k
+            // cycles a tile's accumulator was held - FZ_KERNEL_STATS, DESIGN.md K1.  Per-chunk atomics were 3x slower.)
+            const uint32_t wflags = G.debug == 2 ? 0u : __reduce_or_sync(0xffffffffu, flags);
             if (wflags) {
                 int base = total > 0 ? atomicAdd(&G.st.cnt[q], total) : 0;
                 const size_t off = (size_t)q * G.st.cap;
-#pragma unroll 1
-                for (int c = 0; c < kBN / 32; ++c) {
-                    if (!(wflags & (1u << c))) continue;
-                    ptx::tmem_ld_32x32(t_row + c * 32, ra);
-                    ptx::tmem_ld_wait(ra);
-                    if (flags & (1u << c)) {
+                float* scr = scratch + ((int)threadIdx.x - 128) * 4;          // [8][256 threads] float4: conflict-free STS.128
+                if (wflags & 1u) ptx::tmem_ld_32x32(t_row, ra);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float v = __uint_as_float(ra[j]);
-                            if (v > tau && c * 32 + j < limit) {
-                                if (base < G.st.cap) {
-                                    G.st.score[off + base] = v;
-                                    G.st.id[off + base] = (int32_t)(d0 + c * 32 + j);
-                                }
-                                ++base;
+                for (int c = 0; c < kBN / 32; ++c) {
+                    uint32_t(&cur)[32] = (c & 1) ? rb : ra;
+                    const bool here = (wflags >> c) & 1u;
+                    if (here) ptx::tmem_ld_wait(cur);
+                    if (c + 1 < kBN / 32 && ((wflags >> (c + 1)) & 1u)) ptx::tmem_ld_32x32(t_row + (c + 1) * 32, (c & 1) ? ra : rb);
+                    if (here && masks[c] != 0u) {
+#pragma unroll
+                        for (int k4 = 0; k4 < 8; ++k4)
+                            *reinterpret_cast<uint4*>(scr + k4 * 1024) = make_uint4(cur[4 * k4], cur[4 * k4 + 1], cur[4 * k4 + 2], cur[4 * k4 + 3]);
+                        uint32_t m = masks[c];
+                        while (m) {
+                            const int j = __ffs(m) - 1;
+                            m &= m - 1;
+                            if (base < G.st.cap) {
+                                G.st.score[off + base] = scr[(j >> 2) * 1024 + (j & 3)];
+                                G.st.id[off + base] = (int32_t)(d0 + c * 32 + j);
                             }
+                            ++base;
                         }
                     }
                 }

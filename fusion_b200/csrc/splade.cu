@@ -227,6 +227,7 @@ int fz_splade_topk(const fz_postings_t* tail, const fz_splade_head_t* head, cons
     G.m_tiles = ceil_div(n_queries, kBM);
     G.st = st;
     G.stats = (unsigned long long*)g_debug_stats;
+    if (const char* e = getenv("FZ_DEBUG_GEMM")) G.debug = atoi(e);
     G.codes = (const uint4*)codes;
     G.q_pad = q_pad;
     G.qparam = qparam;

@@ -7,6 +7,7 @@ query -> k-way merge of this rank's query slice; ColBERT rescoring and fusion th
 """
 from __future__ import annotations
 
+import os
 import time
 from dataclasses import dataclass, fields
 
@@ -14,6 +15,10 @@ import torch
 
 from . import ops, sharding
 from .index import DenseIndex, LexicalIndex, SparseIndex, TokenStore
+
+# launch order of the first-stage retrievers (every rank must use the same order: their collectives interleave)
+STAGE_ORDER = tuple(os.environ.get("FZ_STAGE_ORDER", "dpr,splade,bm25").replace(":", ",").split(","))
+assert sorted(STAGE_ORDER) == ["bm25", "dpr", "splade"], STAGE_ORDER
 
 
 @dataclass
@@ -133,33 +138,34 @@ class HybridSearcher:
         # All three first-stage retrievers are LAUNCHED before any per-query status is read back: their fix-ups (overflow /
         # fallback re-runs, rare) run after one host synchronisation per step instead of one per retriever; then the merges.
         local, fixups = {}, []
-        if self.dense is not None:
-            def run_dense():
-                q32, q16 = self.dense.prepare_queries(q.dense)
-                exact = self.dense_exact and self.dense.d_f32 is not None
-                # sharded exact mode: the shards' ceil(k/G)-th scores bound the global k-th one from below, so they agree on
-                # a floor (one all-reduce of Q floats) and rescore only what can still reach the global top-k
-                reduce = (lambda t: sharding.allreduce_min(t, self.group)) if (exact and self.world > 1) else None
-                return ops.dense_topk(q16, self.dense.d_bf16, q32 if exact else None, self.dense.d_f32 if exact else None,
-                                      self.k, margin=self._dense_margin() if exact else 0.0, doc_base=self.dense.doc_base,
-                                      tau_reduce=reduce, n_shards=self.world,
-                                      sched_docs=self._sync["dpr"].sched_docs if (reduce and "dpr" in self._sync) else None,
-                                      defer=True)
-            s, i, fx = self._timed("dpr", run_dense)
-            local["dpr"] = (s, i)
-            fixups.append(fx)
-        if self.sparse is not None:
-            s, i, fx = self._timed("splade", lambda: self.sparse.topk(q.sp_ptr, q.sp_term, q.sp_weight, self.k,
-                                                                       sync=self._sync.get("splade"), defer=True))
-            local["splade"] = (s, i)
-            fixups.append(fx)
-        if self.lexical is not None:
-            s, i, fx = self._timed("bm25", lambda: ops.sparse_topk(self.lexical.view(), q.lex_ptr, q.lex_term, None, self.k,
-                                                                    self.lexical.doc_base, sync=self._sync.get("bm25"), defer=True))
-            local["bm25"] = (s, i)
-            fixups.append(fx)
+
+        def run_dense():
+            q32, q16 = self.dense.prepare_queries(q.dense)
+            exact = self.dense_exact and self.dense.d_f32 is not None
+            # sharded exact mode: the shards' ceil(k/G)-th scores bound the global k-th one from below, so they agree on
+            # a floor (one all-reduce of Q floats) and rescore only what can still reach the global top-k
+            reduce = (lambda t: sharding.allreduce_min(t, self.group)) if (exact and self.world > 1) else None
+            return ops.dense_topk(q16, self.dense.d_bf16, q32 if exact else None, self.dense.d_f32 if exact else None,
+                                  self.k, margin=self._dense_margin() if exact else 0.0, doc_base=self.dense.doc_base,
+                                  tau_reduce=reduce, n_shards=self.world,
+                                  sched_docs=self._sync["dpr"].sched_docs if (reduce and "dpr" in self._sync) else None,
+                                  defer=True)
+
+        stages = {
+            "dpr": (self.dense, run_dense),
+            "splade": (self.sparse, lambda: self.sparse.topk(q.sp_ptr, q.sp_term, q.sp_weight, self.k,
+                                                             sync=self._sync.get("splade"), defer=True)),
+            "bm25": (self.lexical, lambda: ops.sparse_topk(self.lexical.view(), q.lex_ptr, q.lex_term, None, self.k,
+                                                           self.lexical.doc_base, sync=self._sync.get("bm25"), defer=True)),
+        }
+        for name in STAGE_ORDER:
+            index, run = stages[name]
+            if index is not None:
+                s, i, fx = self._timed(name, run)
+                local[name] = (s, i)
+                fixups.append(fx)
         self._timed("status_fixups", lambda: [fx() for fx in fixups])
-        for name in ("dpr", "splade", "bm25"):
+        for name in STAGE_ORDER:
             if name in local:
                 s, i = local[name]
                 out[name] = self._timed(f"{name}_merge", lambda: self._merge(s, i))

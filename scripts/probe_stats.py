@@ -7,7 +7,7 @@ lib = _lib.load()
 dev = torch.device("cuda")
 which = sys.argv[1] if len(sys.argv) > 1 else "maxsim"
 stats = torch.zeros((148, 8), dtype=torch.int64, device=dev)
-names = ["prod_wait_empty", "mma_wait_tempty", "mma_wait_full", "mma_issue", "epi0_wait_tfull", "epi0_total", "epi1_wait_tfull", "epi1_total"]
+names = ["prod_wait_empty", "mma_wait_tempty", "mma_wait_full", "mma_issue", "epi0_wait_tfull", "epi0_total", "epi0_pass2", "epi0_pass2_atomic_wait (plain) / pass2 count (codes)"]
 g = torch.Generator(device=dev); g.manual_seed(1)
 if which == "maxsim":
     nq, nc, pool = 148 * 8, 1000, 200000
