@@ -122,10 +122,6 @@ class HybridSearcher:
             return scores, ids
         return sharding.exchange_merge_topk(scores, ids, self.k, self.group)
 
-    def _dense_margin(self):
-        # |bf16 - fp32 score| <= ~0.004*|q||d| for unit vectors; keep everything within twice that of the k-th score
-        return 0.008 if self.dense_exact else 0.0
-
     # -- pipeline -----------------------------------------------------------------------------------------
     def retrieve(self, q: HybridQueries) -> dict[str, tuple[torch.Tensor, torch.Tensor]]:
         """-> {system: (scores [Qs, k], ids int32 [Qs, k])} for this rank's query slice, best first."""
@@ -146,7 +142,7 @@ class HybridSearcher:
             # a floor (one all-reduce of Q floats) and rescore only what can still reach the global top-k
             reduce = (lambda t: sharding.allreduce_min(t, self.group)) if (exact and self.world > 1) else None
             return ops.dense_topk(q16, self.dense.d_bf16, q32 if exact else None, self.dense.d_f32 if exact else None,
-                                  self.k, margin=self._dense_margin() if exact else 0.0, doc_base=self.dense.doc_base,
+                                  self.k, margin=self.dense.exact_margin(q32, q16) if exact else 0.0, doc_base=self.dense.doc_base,
                                   tau_reduce=reduce, n_shards=self.world,
                                   sched_docs=self._sync["dpr"].sched_docs if (reduce and "dpr" in self._sync) else None,
                                   defer=True)

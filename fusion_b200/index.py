@@ -326,6 +326,7 @@ class DenseIndex:
     d_bf16: torch.Tensor
     similarity: str
     doc_base: int = 0
+    _err: tuple | None = None        # (max |d - bf16(d)|_2, max |d|_2) over the shard's rows
 
     @classmethod
     def build(cls, embeddings: torch.Tensor, similarity: str = "cos_sim", keep_f32: bool = True, doc_base: int = 0):
@@ -355,6 +356,28 @@ class DenseIndex:
 
     def prepare_queries(self, q: torch.Tensor):
         return ops.normalize_rows(q, normalize=self.similarity == "cos_sim")
+
+    def exact_margin(self, q32: torch.Tensor, q16: torch.Tensor) -> float:
+        """How far below the k-th best bf16 score the filter must reach so that exact (fp32) rescoring of the survivors
+        returns the true top-k.  With r = x - bf16(x):  q.d - bf16(q).bf16(d) = r_q.d + bf16(q).r_d, so
+        |error| <= |r_q||d| + |bf16(q)||r_d| (+ the tensor core's fp32 accumulation of exact bf16 products, bounded by
+        dim * 2^-23 * |q||d|); the measured residual norms are ~0.0011 for unit vectors, the worst case 2^-9 per element
+        would be 0.0039.  The cut moves by at most the error on either side, hence twice the bound."""
+        if self.d_f32 is None:
+            return 0.0
+        if self._err is None:
+            e_d, n_d = 0.0, 0.0
+            for lo in range(0, self.d_f32.shape[0], 1 << 18):
+                blk = self.d_f32[lo:lo + (1 << 18)]
+                e_d = max(e_d, float((blk - self.d_bf16[lo:lo + (1 << 18)].float()).norm(dim=1).max()))
+                n_d = max(n_d, float(blk.norm(dim=1).max()))
+            self._err = (e_d, n_d)
+        e_d, n_d = self._err
+        q16f = q16.float()
+        e_q = float((q32 - q16f).norm(dim=1).max())
+        n_q = max(float(q32.norm(dim=1).max()), float(q16f.norm(dim=1).max()))
+        err = e_q * n_d + n_q * e_d + q32.shape[1] * 2.0 ** -23 * n_q * n_d
+        return 2.0 * err * (1.0 + 1e-3)
 
 
 @dataclass

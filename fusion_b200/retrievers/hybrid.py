@@ -110,10 +110,7 @@ class Ranker:
                 out_s[lo:lo + step], out_i[lo:lo + step] = ops.rank_rows(sc, k, index.doc_base)
             return out_s, out_i
         if margin is None:
-            # |bf16 score - fp32 score| <= (2*2^-9 + 2^-18) * |q||d| (+ fp32 accumulation); both sides of the cut => 2x
-            qn = float(q32.norm(dim=1).max())
-            dn = 1.0 if index.similarity == "cos_sim" else float(index.d_f32.norm(dim=1).max())
-            margin = 2 * 0.004 * qn * dn if exact else 0.0
+            margin = index.exact_margin(q32, q16) if exact else 0.0      # from the measured bf16 residual norms
         return ops.dense_topk(q16, index.d_bf16, q32 if exact else None, index.d_f32 if exact else None, k,
                               margin=margin, doc_base=index.doc_base)
 
