@@ -59,7 +59,9 @@ struct GemmArgs {
     unsigned long long* stats;   // optional [gridDim.x, 8] cycle counters (fz_debug_set_stats)
     int debug;                   // FZ_DEBUG_GEMM timing probes (results are WRONG): 1 = nothing passes, 2 = no appends
     // kCodes only
-    const uint4* codes;          // [(n_tiles * 8 + chunk) * q_pad + q]: the 32 codes of (query q, 32-doc chunk)
+    const uint4* codes;          // [(256-doc tile of the round) * q_pad + q][8]: the 32 codes of (query q, 32-doc chunk); the 8
+                                 // chunks of a tile are one 128-byte line: the tail kernel stores whole lines, the epilogue
+                                 // warp reads its 32 queries' lines as one contiguous 4 KB
     int q_pad;                   // n_queries rounded up to kBM
     const float2* qparam;        // [n_queries] (gh, g): head gain incl. the bf16 error allowance, tail gain
 };
@@ -270,9 +272,12 @@ filter_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
             // codes of this (query, doc tile): issued before the wait for the accumulator, which hides their latency
             uint4 cw[kCodes ? kBN / 32 : 1];
             if constexpr (kCodes) {
-                const uint4* cp = G.codes + ((size_t)n_t * (kBN / 32)) * G.q_pad + (size_t)(m_t * kBM + ew * 32 + lane);
+                // the 8 chunks of (query, 256-doc tile) are one 128-byte line and the lines of a tile's queries are adjacent:
+                // the warp fetches its 32 lines as 8 fully coalesced loads (load c: rows 4 c + lane / 8, 16-byte column
+                // lane % 8) and transposes them through shared memory once the accumulator is there
+                const uint4* cp = G.codes + ((size_t)n_t * G.q_pad + (size_t)(m_t * kBM + ew * 32)) * (kBN / 32) + lane;
 #pragma unroll
-                for (int c = 0; c < kBN / 32; ++c) cw[c] = __ldg(cp + (size_t)c * G.q_pad);
+                for (int c = 0; c < kBN / 32; ++c) cw[c] = __ldg(cp + 32 * c);
             }
             const long long t0 = FZ_CLOCK();
             ptx::mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
@@ -281,6 +286,18 @@ filter_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
             const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)buf * kBN;
             uint32_t ra[32], rb[32];
             if constexpr (kCodes) {
+                {   // transpose: row r, column c is parked at column c ^ (r & 7) - conflict-free both ways
+                    uint4* sw = reinterpret_cast<uint4*>(scratch) + (warp - 4) * 256;
+#pragma unroll
+                    for (int c = 0; c < kBN / 32; ++c) {
+                        const int r = 4 * c + (lane >> 3);
+                        sw[r * 8 + ((lane & 7) ^ (r & 7))] = cw[c];
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int c = 0; c < kBN / 32; ++c) cw[c] = sw[lane * 8 + (c ^ (lane & 7))];
+                    __syncwarp();
+                }
                 // Branch-free: lanes are different queries, so "some lane of the warp has a survivor in this chunk" is the
                 // normal case and a warp-level slow path would run almost always.  Every element costs the decode (shift +
                 // LOP3), one FFMA and a compare folded into the survivor mask; no max tree, no second pass over TMEM.

@@ -605,7 +605,7 @@ __global__ void __launch_bounds__(kTailThreads) tail_codes_kernel(const TailCode
     for (int i = t * 4; i < tile_docs / 8; i += kTailThreads * 4) *reinterpret_cast<uint4*>(cs + i) = make_uint4(0, 0, 0, 0);
     const float gain = T.qparam[q].y * kTailScale;
     const long long r_hi_pad = (T.r_hi + 255) / 256 * 256;
-    uint4* __restrict__ out4 = reinterpret_cast<uint4*>(T.codes) + q;       // [(doc - r_lo) / 32][q_pad] x 16 bytes
+    uint4* __restrict__ out4 = reinterpret_cast<uint4*>(T.codes);           // [((doc - r_lo) / 256) * q_pad + q][8] x 16 bytes
     __syncthreads();
     const int n_tw = S.n <= 32 ? 1 : (S.n + 31) >> 5;
     uint32_t o0 = tile_offset<float>(A, S, t_begin), o1 = tile_offset<float>(A, S, t_begin + 1);
@@ -652,7 +652,7 @@ __global__ void __launch_bounds__(kTailThreads) tail_codes_kernel(const TailCode
         __syncthreads();        // list visible (accumulators are zero: set-up / the previous tile's encode pass)
 
         // ---- scatter: warp w takes terms w, w + 8, ...; integer atomics, no barrier between terms
-        const int n_active = Lt.n;
+        const int n_active = (T.debug & 2) ? 0 : Lt.n;
         const int dl = (int)d_lo;
         for (int j = warp; j < n_active; j += n_warps) {
             const int jlk = Lt.lenkind[j];
@@ -711,16 +711,17 @@ __global__ void __launch_bounds__(kTailThreads) tail_codes_kernel(const TailCode
         }
         __syncthreads();
 
-        // ---- the tile's code words -> the layout the GEMM epilogue reads: 16 bytes per (32-doc chunk, query); the words
-        // are zeroed again by the thread that copied them
+        // ---- the tile's code words -> the round's code buffer [256-doc tile][query][8 chunks]: 8 consecutive threads store
+        // one whole 128-byte line (a [chunk][query] layout cost 1.9 G scattered 16-byte partial-sector stores per step: 10
+        // of this kernel's 46 ms); the words are zeroed again by the thread that copied them
         {
             const long long c_lo = max(d_lo, T.r_lo), c_hi = min(d_lo + tile_docs, r_hi_pad);      // multiples of 256
             const int i_lo = (int)((c_lo - d_lo) >> 5), i_hi = (int)((c_hi - d_lo) >> 5);
-            // (may point below the buffer when the round starts inside the tile: only [i_lo, i_hi) is touched)
-            uint4* __restrict__ dst = out4 + ((d_lo - T.r_lo) >> 5) * (long long)T.q_pad;
+            const long long rel = (d_lo - T.r_lo) >> 5;          // chunk index of the tile's first doc in the round (may be < 0)
             for (int i = i_lo + t; i < i_hi; i += kTailThreads) {
                 uint4* src = reinterpret_cast<uint4*>(cs) + i;
-                dst[(long long)i * T.q_pad] = *src;
+                const long long ch = rel + i;
+                if (!(T.debug & 1)) out4[((ch >> 3) * T.q_pad + q) * 8 + (ch & 7)] = *src;
                 *src = make_uint4(0, 0, 0, 0);
             }
         }

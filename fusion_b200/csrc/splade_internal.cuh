@@ -15,7 +15,7 @@ struct TailCodeArgs {
     int q_pad;                   // n_queries rounded up to 128
     long long r_lo, r_hi;        // doc range of the round; r_lo % 256 == 0
     const float2* qparam;        // [n_queries] (gh, g)
-    uint32_t* codes;             // [((r_hi - r_lo + 255) / 256 * 8 + chunk) * q_pad + q] x 4 words of 8 codes
+    uint32_t* codes;             // [((doc - r_lo) / 256) * q_pad + q][8] x 4 words of 8 codes (GemmArgs::codes)
     int32_t* status;             // FZ_STATUS_FALLBACK when a tail sum left the code range
     int debug;                   // timing experiments only (FZ_DEBUG_TAIL): 1 = no global stores, 2 = no posting walk
 };

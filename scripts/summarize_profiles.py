@@ -69,7 +69,8 @@ def kernels(rnd):
                     ("dense_filter_gemm", "prof_dense"), ("maxsim", "prof_maxsim")],
             "r02": [("sparse_tile_f64", "prof_r02_sparse_f64"), ("dense_filter_gemm", "prof_r02_dense"), ("maxsim", "prof_r02_maxsim"),
                     ("splade_head_gemm", "prof_r02_head_gemm"), ("splade_tail_codes", "prof_r02_tail_codes"),
-                    ("splade_rescore", "prof_r02_rescore")]}
+                    ("splade_rescore", "prof_r02_rescore")],
+            "r02b": [("dense_filter_gemm", "prof_r02b_dense")]}
     for tag, rep in reps.get(rnd, reps["r02"]):
         path = os.path.join(SRC, rep + ".ncu-rep")
         if not os.path.exists(path):
@@ -88,7 +89,10 @@ def kernels(rnd):
                             "round": rnd, "launch": f"largest round of one step (ncu -s index in scripts/gpu_profile{'_r02' if rnd != 'r01' else ''}.sh)"}
             print(tag, traffic[tag])
     if traffic:
-        json.dump(traffic, open(os.path.join(OUT, "traffic.json"), "w"), indent=1)
+        tj = os.path.join(OUT, "traffic.json")
+        old = json.load(open(tj)) if os.path.exists(tj) else {}
+        old.update(traffic)            # a follow-up round re-captures only the kernels that changed
+        json.dump(old, open(tj, "w"), indent=1)
 
 
 if __name__ == "__main__":
