@@ -57,7 +57,7 @@ struct GemmArgs {
     int m_tiles, n_tiles;
     CandState<float> st;
     unsigned long long* stats;   // optional [gridDim.x, 8] cycle counters (fz_debug_set_stats)
-    int debug;                   // FZ_DEBUG_GEMM timing probes (results are WRONG): 1 = nothing passes, 2 = no appends
+    int debug;                   // FZ_DEBUG_GEMM timing probes (results are WRONG): 1 = nothing passes, 2 = no appends; codes mode: 3 = no filter arithmetic, 4 = no TMEM reads either
     // kCodes only
     const uint4* codes;          // [(256-doc tile of the round) * q_pad + q][8]: the 32 codes of (query q, 32-doc chunk); the 8
                                  // chunks of a tile are one 128-byte line: the tail kernel stores whole lines, the epilogue
@@ -259,6 +259,27 @@ filter_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
                 thr = G.debug == 1 ? std::numeric_limits<float>::infinity() : tau;
             }
         };
+        // codes mode: the 8 chunks of (query, 256-doc tile) are one 128-byte line and the lines of a tile's queries are
+        // adjacent, so the warp's 32 lines are one contiguous 4 KB.  They are copied global -> shared with cp.async ONE TILE
+        // AHEAD (copy c of a lane: row 4 c + lane / 8, 16-byte column lane % 8, parked at column ^ (row & 7): conflict-free
+        // for the copy and for the transposed read) - the epilogue is the bottleneck of this kernel, so the accumulator is
+        // always ready and a load issued at the top of a tile had its whole latency (thousands of cycles under load) exposed.
+        auto issue_codes = [&](int tile) {
+            if constexpr (kCodes) {
+                if (tile < total_tiles) {
+                    const int n_t = tile / m_pairs, m_t = (tile - n_t * m_pairs) * kPair + crank;
+                    const uint4* cp = G.codes + ((size_t)n_t * G.q_pad + (size_t)(m_t * kBM + ew * 32)) * (kBN / 32) + lane;
+                    uint4* sw = reinterpret_cast<uint4*>(scratch) + (warp - 4) * 256;
+#pragma unroll
+                    for (int c = 0; c < kBN / 32; ++c) {
+                        const int r = 4 * c + (lane >> 3);
+                        ptx::cp_async_16(sw + r * 8 + ((lane & 7) ^ (r & 7)), cp + 32 * c);
+                    }
+                }
+                ptx::cp_async_commit();
+            }
+        };
+        issue_codes(cluster_id + team * n_clusters);
         float thr_next, gh_next;
         par_of(cluster_id + team * n_clusters, thr_next, gh_next);
         for (int tile = cluster_id + team * n_clusters; tile < total_tiles; tile += 2 * n_clusters, it += 2) {
@@ -269,16 +290,7 @@ filter_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
             const int limit = (int)min((long long)kBN, G.r_hi - d0);
             const float tau = thr_next, gh = gh_next;
             par_of(tile + 2 * n_clusters, thr_next, gh_next);
-            // codes of this (query, doc tile): issued before the wait for the accumulator, which hides their latency
             uint4 cw[kCodes ? kBN / 32 : 1];
-            if constexpr (kCodes) {
-                // the 8 chunks of (query, 256-doc tile) are one 128-byte line and the lines of a tile's queries are adjacent:
-                // the warp fetches its 32 lines as 8 fully coalesced loads (load c: rows 4 c + lane / 8, 16-byte column
-                // lane % 8) and transposes them through shared memory once the accumulator is there
-                const uint4* cp = G.codes + ((size_t)n_t * G.q_pad + (size_t)(m_t * kBM + ew * 32)) * (kBN / 32) + lane;
-#pragma unroll
-                for (int c = 0; c < kBN / 32; ++c) cw[c] = __ldg(cp + 32 * c);
-            }
             const long long t0 = FZ_CLOCK();
             ptx::mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
             st_wait_tfull += FZ_CLOCK() - t0;
@@ -286,42 +298,77 @@ filter_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
             const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)buf * kBN;
             uint32_t ra[32], rb[32];
             if constexpr (kCodes) {
-                {   // transpose: row r, column c is parked at column c ^ (r & 7) - conflict-free both ways
-                    uint4* sw = reinterpret_cast<uint4*>(scratch) + (warp - 4) * 256;
-#pragma unroll
-                    for (int c = 0; c < kBN / 32; ++c) {
-                        const int r = 4 * c + (lane >> 3);
-                        sw[r * 8 + ((lane & 7) ^ (r & 7))] = cw[c];
-                    }
+                {   // this tile's codes were copied into the warp's scratch a whole tile ago (issue_codes); fetch the next
+                    // tile's as soon as this one's are in registers
+                    ptx::cp_async_wait_all();
                     __syncwarp();
+                    const uint4* sw = reinterpret_cast<const uint4*>(scratch) + (warp - 4) * 256;
 #pragma unroll
                     for (int c = 0; c < kBN / 32; ++c) cw[c] = sw[lane * 8 + (c ^ (lane & 7))];
                     __syncwarp();
+                    issue_codes(tile + 2 * n_clusters);
                 }
                 // Branch-free: lanes are different queries, so "some lane of the warp has a survivor in this chunk" is the
-                // normal case and a warp-level slow path would run almost always.  Every element costs the decode (shift +
-                // LOP3), one FFMA and a compare folded into the survivor mask; no max tree, no second pass over TMEM.
+                // normal case and a warp-level slow path would run almost always.  Every element costs a shift, ONE lop3
+                // ((shifted word & field) | exponent; the constants are held in registers - as immediates they cost a second
+                // LOP3 on the half-rate INT pipe), one FFMA, and the survivor bit accumulated on the FMA pipe: (x > tau) as
+                // 0.0 / 1.0 times 2^j into two fp32 sums of 16 exact bits each.  No max tree, no second pass over TMEM.
+                // The chunk loop is ROLLED (two chunks per iteration, register arrays rotated instead of indexed): fully
+                // unrolled, the epilogue was 70 KB of code that every warp streamed through once per tile, and a third of
+                // all warp samples were instruction-fetch stalls (ncu `stall_no_inst`, profiles/r02d_splade_head_gemm.md).
                 uint32_t masks[kBN / 32];
+                uint32_t k_field, k_base;
+                asm volatile("mov.u32 %0, 0x03C00000;" : "=r"(k_field));
+                asm volatile("mov.u32 %0, 0x3C000000;" : "=r"(k_base));
                 const bool collect_all = !(tau > -std::numeric_limits<float>::infinity());   // no threshold yet (first rounds)
-                ptx::tmem_ld_32x32(t_row, ra);
-#pragma unroll
-                for (int c = 0; c < kBN / 32; ++c) {
-                    uint32_t(&cur)[32] = (c & 1) ? rb : ra;
-                    ptx::tmem_ld_wait(cur);
-                    if (c + 1 < kBN / 32) ptx::tmem_ld_32x32(t_row + (c + 1) * 32, (c & 1) ? ra : rb);
-                    const uint32_t w4[4] = {cw[c].x, cw[c].y, cw[c].z, cw[c].w};
+                auto chunk_mask = [&](const uint32_t(&cur)[32], const uint4 cwc, int c) -> uint32_t {
+                    const uint32_t w4[4] = {cwc.x, cwc.y, cwc.z, cwc.w};
                     uint32_t mask = 0;
+                    if (G.debug >= 3) return 0u;
                     if (!collect_all) {
+                        float lo16 = 0.0f, hi16 = 0.0f;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (fmaf(__uint_as_float(cur[j]), gh, code_decode(w4[j >> 3], j & 7)) > tau) mask |= 1u << j;
+                        for (int j = 0; j < 32; ++j) {
+                            const int nib = j & 7;
+                            const uint32_t word = w4[j >> 3];
+                            const uint32_t sh = nib <= 5 ? (word << (22 - 4 * nib)) : (word >> (4 * nib - 22));
+                            uint32_t dec;
+                            asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(dec) : "r"(sh), "r"(k_field), "r"(k_base));
+                            const float x = fmaf(__uint_as_float(cur[j]), gh, __uint_as_float(dec));
+                            const float hit = x > tau ? 1.0f : 0.0f;
+                            if (j < 16) lo16 = fmaf(hit, (float)(1u << j), lo16);
+                            else hi16 = fmaf(hit, (float)(1u << (j - 16)), hi16);
+                        }
+                        mask = (uint32_t)lo16 | ((uint32_t)hi16 << 16);
                     } else {
                         // every doc of the round that shares a term with the query (head != 0 or code != 0)
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
                             if ((cur[j] != 0u || ((w4[j >> 3] >> (4 * (j & 7))) & 15u) != 0u) && c * 32 + j < limit) mask |= 1u << j;
                     }
-                    masks[c] = mask;
+                    return mask;
+                };
+                if (G.debug != 4) ptx::tmem_ld_32x32(t_row, ra);
+#pragma unroll 1
+                for (int c = 0; c < kBN / 32; c += 2) {
+                    if (G.debug != 4) {
+                        ptx::tmem_ld_wait(ra);
+                        ptx::tmem_ld_32x32(t_row + (c + 1) * 32, rb);
+                    }
+                    const uint32_t me = chunk_mask(ra, cw[0], c);
+                    if (G.debug != 4) {
+                        ptx::tmem_ld_wait(rb);
+                        if (c + 2 < kBN / 32) ptx::tmem_ld_32x32(t_row + (c + 2) * 32, ra);
+                    }
+                    const uint32_t mo = chunk_mask(rb, cw[1], c + 1);
+                    // rotate: the next iteration finds its codes in cw[0..1]; after the last one masks[] is in chunk order
+#pragma unroll
+                    for (int i = 0; i + 2 < kBN / 32; ++i) {
+                        cw[i] = cw[i + 2];
+                        masks[i] = masks[i + 2];
+                    }
+                    masks[kBN / 32 - 2] = me;
+                    masks[kBN / 32 - 1] = mo;
                 }
                 // The survivors are rescored exactly afterwards, so only their doc ids are recorded: the accumulator is
                 // released BEFORE the slot-reserving atomic (its round trip is off the tensor pipe's critical path) and the
