@@ -403,15 +403,11 @@ filter_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
             }
             // Pass 1: each 32-column chunk is reduced with a max TREE (no dependent chain) while the next chunk's
             // tcgen05.ld is already in flight; only a chunk whose maximum beats tau pays for the compare mask.
+            // Both passes are ROLLED loops over chunk pairs (mask registers rotated instead of indexed): see the codes path.
             uint32_t masks[kBN / 32];
             uint32_t flags = 0;
             int total = 0;
-            ptx::tmem_ld_32x32(t_row, ra);
-#pragma unroll
-            for (int c = 0; c < kBN / 32; ++c) {
-                uint32_t(&cur)[32] = (c & 1) ? rb : ra;
-                ptx::tmem_ld_wait(cur);
-                if (c + 1 < kBN / 32) ptx::tmem_ld_32x32(t_row + (c + 1) * 32, (c & 1) ? ra : rb);
+            auto chunk_mask = [&](const uint32_t(&cur)[32], int c) -> uint32_t {
                 float m8[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
@@ -425,11 +421,23 @@ filter_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
                     for (int j = 0; j < 32; ++j)
                         if (__uint_as_float(cur[j]) > tau && c * 32 + j < limit) mask |= 1u << j;
                 }
-                masks[c] = mask;
-                if (mask) {
-                    flags |= 1u << c;
-                    total += __popc(mask);
-                }
+                return mask;
+            };
+            ptx::tmem_ld_32x32(t_row, ra);
+#pragma unroll 1
+            for (int c = 0; c < kBN / 32; c += 2) {
+                ptx::tmem_ld_wait(ra);
+                ptx::tmem_ld_32x32(t_row + (c + 1) * 32, rb);
+                const uint32_t me = chunk_mask(ra, c);
+                ptx::tmem_ld_wait(rb);
+                if (c + 2 < kBN / 32) ptx::tmem_ld_32x32(t_row + (c + 2) * 32, ra);
+                const uint32_t mo = chunk_mask(rb, c + 1);
+#pragma unroll
+                for (int i = 0; i + 2 < kBN / 32; ++i) masks[i] = masks[i + 2];
+                masks[kBN / 32 - 2] = me;
+                masks[kBN / 32 - 1] = mo;
+                flags |= ((me != 0u ? 1u : 0u) | (mo != 0u ? 2u : 0u)) << c;
+                total += __popc(me) + __popc(mo);
             }
             const long long tp2 = FZ_CLOCK();
             // Pass 2: one atomic per thread and tile reserves the slots; the flagged chunks (warp-wide union: tcgen05.ld is
@@ -443,28 +451,32 @@ filter_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
                 int base = total > 0 ? atomicAdd(&G.st.cnt[q], total) : 0;
                 const size_t off = (size_t)q * G.st.cap;
                 float* scr = scratch + ((int)threadIdx.x - 128) * 4;          // [8][256 threads] float4: conflict-free STS.128
-                if (wflags & 1u) ptx::tmem_ld_32x32(t_row, ra);
+                auto emit = [&](const uint32_t(&cur)[32], uint32_t m, int c) {
 #pragma unroll
-                for (int c = 0; c < kBN / 32; ++c) {
-                    uint32_t(&cur)[32] = (c & 1) ? rb : ra;
-                    const bool here = (wflags >> c) & 1u;
-                    if (here) ptx::tmem_ld_wait(cur);
-                    if (c + 1 < kBN / 32 && ((wflags >> (c + 1)) & 1u)) ptx::tmem_ld_32x32(t_row + (c + 1) * 32, (c & 1) ? ra : rb);
-                    if (here && masks[c] != 0u) {
-#pragma unroll
-                        for (int k4 = 0; k4 < 8; ++k4)
-                            *reinterpret_cast<uint4*>(scr + k4 * 1024) = make_uint4(cur[4 * k4], cur[4 * k4 + 1], cur[4 * k4 + 2], cur[4 * k4 + 3]);
-                        uint32_t m = masks[c];
-                        while (m) {
-                            const int j = __ffs(m) - 1;
-                            m &= m - 1;
-                            if (base < G.st.cap) {
-                                G.st.score[off + base] = scr[(j >> 2) * 1024 + (j & 3)];
-                                G.st.id[off + base] = (int32_t)(d0 + c * 32 + j);
-                            }
-                            ++base;
+                    for (int k4 = 0; k4 < 8; ++k4)
+                        *reinterpret_cast<uint4*>(scr + k4 * 1024) = make_uint4(cur[4 * k4], cur[4 * k4 + 1], cur[4 * k4 + 2], cur[4 * k4 + 3]);
+                    while (m) {
+                        const int j = __ffs(m) - 1;
+                        m &= m - 1;
+                        if (base < G.st.cap) {
+                            G.st.score[off + base] = scr[(j >> 2) * 1024 + (j & 3)];
+                            G.st.id[off + base] = (int32_t)(d0 + c * 32 + j);
                         }
+                        ++base;
                     }
+                };
+                if (wflags & 1u) ptx::tmem_ld_32x32(t_row, ra);
+#pragma unroll 1
+                for (int c = 0; c < kBN / 32; c += 2) {
+                    const bool h0 = (wflags >> c) & 1u, h1 = (wflags >> (c + 1)) & 1u;
+                    if (h0) ptx::tmem_ld_wait(ra);
+                    if (h1) ptx::tmem_ld_32x32(t_row + (c + 1) * 32, rb);
+                    if (h0 && masks[0] != 0u) emit(ra, masks[0], c);
+                    if (h1) ptx::tmem_ld_wait(rb);
+                    if (c + 2 < kBN / 32 && ((wflags >> (c + 2)) & 1u)) ptx::tmem_ld_32x32(t_row + (c + 2) * 32, ra);
+                    if (h1 && masks[1] != 0u) emit(rb, masks[1], c + 1);
+#pragma unroll
+                    for (int i = 0; i + 2 < kBN / 32; ++i) masks[i] = masks[i + 2];
                 }
                 st_pass2 += FZ_CLOCK() - tp2;
                 ++st_pass2_n;
