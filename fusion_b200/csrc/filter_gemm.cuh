@@ -235,19 +235,27 @@ filter_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         // takes thousands of cycles and would otherwise sit between "accumulator ready" and "accumulator released".
         // -> (threshold, head gain): plain mode (tau, 1); codes mode (tau * g + B0 nudged down, gh).  A query without k
         // positive-score docs yet (tau <= 0) takes every doc that matches anything: threshold -inf.
-        auto par_of = [&](int tile, float& thr, float& gh) {
-            thr = std::numeric_limits<float>::infinity();
-            gh = 1.0f;
+        // par_load only LOADS (tau, gh, g) of the next tile's query; par_finish turns them into the threshold at the top of
+        // the next iteration - with the arithmetic (and its branch) next to the load, the warp waited out the load's whole
+        // latency every tile (9 % of the head GEMM's warp samples, profiles/r02_stall_sampling.md).
+        auto par_load = [&](int tile, float& tau_raw, float2& p) {
+            tau_raw = std::numeric_limits<float>::infinity();      // marks "no query": nothing passes
+            p = make_float2(1.0f, 1.0f);
             if (tile >= total_tiles) return;
             const int n_t = tile / m_pairs, m_t = (tile - n_t * m_pairs) * kPair + crank;
             const int q = m_t * kBM + ew * 32 + lane;
             if (q >= G.n_queries) return;
-            const float tau = G.st.tau[q];
+            tau_raw = G.st.tau[q];
+            if constexpr (kCodes) p = G.qparam[q];
+        };
+        auto par_finish = [&](float tau_raw, float2 p, float& thr, float& gh) {
+            gh = 1.0f;
             if constexpr (kCodes) {
-                const float2 p = G.qparam[q];
                 gh = p.x;
-                if (tau > 0.0f) {
-                    const float t = fmaf(tau, p.y, kCodeB0);
+                if (tau_raw == std::numeric_limits<float>::infinity()) {
+                    thr = tau_raw;
+                } else if (tau_raw > 0.0f) {
+                    const float t = fmaf(tau_raw, p.y, kCodeB0);
                     // the fma below rounds (2^-24 relative): never lose a borderline doc.  Never below B0: a doc that
                     // shares no term with the query (head 0, code 0; also the zero-filled rows past the last doc)
                     // evaluates to exactly B0 and must not pass.
@@ -256,7 +264,7 @@ filter_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
                     thr = -std::numeric_limits<float>::infinity();
                 }
             } else {
-                thr = G.debug == 1 ? std::numeric_limits<float>::infinity() : tau;
+                thr = G.debug == 1 ? std::numeric_limits<float>::infinity() : tau_raw;
             }
         };
         // codes mode: the 8 chunks of (query, 256-doc tile) are one 128-byte line and the lines of a tile's queries are
@@ -280,16 +288,18 @@ filter_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
             }
         };
         issue_codes(cluster_id + team * n_clusters);
-        float thr_next, gh_next;
-        par_of(cluster_id + team * n_clusters, thr_next, gh_next);
+        float tau_next;
+        float2 p_next;
+        par_load(cluster_id + team * n_clusters, tau_next, p_next);
         for (int tile = cluster_id + team * n_clusters; tile < total_tiles; tile += 2 * n_clusters, it += 2) {
             const int n_t = tile / m_pairs, m_t = (tile - n_t * m_pairs) * kPair + crank;
             const int buf = it & 1;
             const int q = m_t * kBM + ew * 32 + lane;
             const long long d0 = G.r_lo + (long long)n_t * kBN;
             const int limit = (int)min((long long)kBN, G.r_hi - d0);
-            const float tau = thr_next, gh = gh_next;
-            par_of(tile + 2 * n_clusters, thr_next, gh_next);
+            float tau, gh;
+            par_finish(tau_next, p_next, tau, gh);
+            par_load(tile + 2 * n_clusters, tau_next, p_next);
             uint4 cw[kCodes ? kBN / 32 : 1];
             const long long t0 = FZ_CLOCK();
             ptx::mbar_wait(&tfull_bar[buf], (it >> 1) & 1);

@@ -70,8 +70,9 @@ def kernels(rnd):
             "r02": [("sparse_tile_f64", "prof_r02_sparse_f64"), ("dense_filter_gemm", "prof_r02_dense"), ("maxsim", "prof_r02_maxsim"),
                     ("splade_head_gemm", "prof_r02_head_gemm"), ("splade_tail_codes", "prof_r02_tail_codes"),
                     ("splade_rescore", "prof_r02_rescore")],
-            "r02b": [("dense_filter_gemm", "prof_r02b_dense")]}
-    for tag, rep in reps.get(rnd, reps["r02"]):
+            "r02b": [("dense_filter_gemm", "prof_r02b_dense")],
+            "r02f": [("splade_head_gemm", "prof_r02f_head_gemm")]}
+    for tag, rep in reps.get(rnd, []):
         path = os.path.join(SRC, rep + ".ncu-rep")
         if not os.path.exists(path):
             continue
