@@ -76,3 +76,29 @@ def test_header_is_plain_c_and_layouts_match_ctypes(tmp_path):
                    _lib.Postings.dense_stride.offset, ctypes.sizeof(_lib.SpladeHead), _lib.SpladeHead.head_dim.offset,
                    _lib.SpladeHead.flags.offset, ctypes.sizeof(_lib.BuildPlan), _lib.BuildPlan.n_tiled.offset,
                    _lib.BuildPlan.n_coarse.offset]
+
+
+def test_a_plain_c_host_links_and_calls_the_library(tmp_path):
+    """What a cgo / JNI shim does: a C99 program includes the header, links libfusion_b200.so and calls entry points - here
+    the ones that need no GPU (ABI version, an argument error with its message, a workspace-size query)."""
+    import shutil
+    import subprocess
+    from fusion_b200 import _lib, build
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    lib_path = build.build()
+    src = tmp_path / "host.c"
+    src.write_text('#include <stdio.h>\n#include <string.h>\n#include "fusion_b200.h"\n'
+                   'int main(void) {\n'
+                   '  fz_build_plan_t plan; memset(&plan, 0, sizeof plan);\n'
+                   '  int rc = fz_build_postings_plan(NULL, NULL, 0, 0, 1024, 512, 1 << 20, NULL, NULL, &plan, NULL, 0, NULL);\n'
+                   '  printf("%d %d %zu %s\\n", fz_abi_version(), rc, fz_build_postings_workspace_bytes(1000), fz_last_error());\n'
+                   '  return 0; }\n')
+    exe = tmp_path / "host"
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                    "-L", os.path.dirname(lib_path), "-lfusion_b200", "-Wl,-rpath," + os.path.dirname(lib_path)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split(None, 3)
+    assert int(out[0]) == _lib.ABI_VERSION
+    assert int(out[1]) == -1 and "fz_build_postings_plan" in out[3]
+    assert int(out[2]) > 0
