@@ -638,6 +638,8 @@ def build_postings(term_ptr: torch.Tensor, post_doc: torch.Tensor, post_val: tor
 def build_csr_normalize(doc_ptr: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
     lib = _lib.load()
     out = torch.empty_like(weight)
+    if weight.numel() == 0:          # every row is empty: nothing to normalise
+        return out
     check(lib.fz_build_csr_normalize(_ptr(_req(doc_ptr, torch.int64, "doc_ptr")), _ptr(_req(weight, torch.float32, "weight")),
                                      doc_ptr.numel() - 1, _ptr(out), _stream(weight)), "fz_build_csr_normalize")
     return out
