@@ -682,8 +682,10 @@ extern "C" int fz_build_term_stats(const int32_t* term, const float* weight, int
                                    float* out_term_max, int32_t* out_flags, fz_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     FZ_REQUIRE(nnz >= 0 && n_terms >= 0 && out_flags && (n_terms == 0 || (out_df && out_term_max)), "fz_build_term_stats: bad arguments");
-    FZ_CUDA(cudaMemsetAsync(out_df, 0, (size_t)n_terms * 8, stream));
-    FZ_CUDA(cudaMemsetAsync(out_term_max, 0, (size_t)n_terms * 4, stream));
+    if (n_terms > 0) {
+        FZ_CUDA(cudaMemsetAsync(out_df, 0, (size_t)n_terms * 8, stream));
+        FZ_CUDA(cudaMemsetAsync(out_term_max, 0, (size_t)n_terms * 4, stream));
+    }
     FZ_CUDA(cudaMemsetAsync(out_flags, 0, 4, stream));
     if (nnz == 0) return FZ_OK;
     FZ_REQUIRE(term && weight, "fz_build_term_stats: null input");
